@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference controller classes over the C ABI (Python flavour, used by tests and bench).
+
+Same class names, parameter names/defaults and per-cycle method names as the reference nodes
+(include/ccv_mppi_path_tracker/{diff_drive,steering_diff_drive,full_body}_mppi.h); ROS I/O is replaced by plain
+attributes: `set_path()` stands for pathCallback, `current_state` for get_Transform / get_CurrentState, and
+`solve()` for one pass of run()'s `sampling(); predict_States(); calc_Weights(); determine_OptimalSolution();`.
+The C++ equivalents used by the harness live in csrc/host/controllers.hpp.  All compute happens in
+libmppi_b200.so on the GPU; nothing here falls back to the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .params import MODEL_ID, NUM_CONTROLS, NUM_STATES, node_params, solve_params
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class _MPPIBase:
+    MODEL = None
+
+    def __init__(self, launch=True, n_robots=1, device=0, **overrides):
+        self.lib = _capi.load()
+        self.p = node_params(self.MODEL, launch=launch, **overrides)
+        self.model = self.MODEL
+        self.horizon_ = int(self.p["horizon"])
+        self.num_samples_ = int(self.p["num_samples"])
+        self.dt_ = float(self.p["dt"])
+        self.U = NUM_CONTROLS[self.MODEL]
+        self.S = NUM_STATES[self.MODEL]
+        self.n_robots = int(n_robots)
+        self._h = C.c_void_p()
+        cp = self._cparams()
+        rc = self.lib.mppi_create(C.byref(self._h), MODEL_ID[self.MODEL], C.byref(cp), self.num_samples_,
+                                  self.horizon_, self.n_robots, device)
+        if rc != 0:
+            raise _capi.MppiError(rc, self.lib.mppi_last_error(None).decode())
+        # optimal_solution (DDh:100): [n_robots][T-1][U], zero-initialised like RobotStates::init
+        self.optimal_solution = np.zeros((self.n_robots, self.horizon_ - 1, self.U), dtype=np.float64)
+        self.current_state = np.zeros((self.n_robots, self.S), dtype=np.float64)
+
+    # -- plumbing ---------------------------------------------------------------------------------------
+    def _cparams(self):
+        sp = solve_params(self.MODEL, self.p)
+        cp = _capi.MppiParams()
+        for k, v in sp.items():
+            if k in ("u_min", "u_max"):
+                setattr(cp, k, (C.c_double * 5)(*v))
+            else:
+                setattr(cp, k, v)
+        return cp
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _capi.MppiError(rc, self.lib.mppi_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.mppi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- inputs -----------------------------------------------------------------------------------------
+    def set_param(self, **kw):
+        self.p.update(kw)
+        cp = self._cparams()
+        self._check(self.lib.mppi_set_params(self._h, C.byref(cp)))
+
+    def set_path(self, xy, robot=0):
+        """pathCallback: the full reference path (N x 2)."""
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        self._check(self.lib.mppi_set_path(self._h, robot, _dptr(xy), xy.shape[0]))
+
+    def set_window(self, window, robot=0):
+        w = np.ascontiguousarray(window, dtype=np.float64).reshape(self.horizon_, 3)
+        self._check(self.lib.mppi_set_window(self._h, robot, _dptr(w)))
+
+    def set_seed(self, seed, counter=0):
+        self._check(self.lib.mppi_set_seed(self._h, seed, counter))
+
+    def set_shard(self, sample_offset, num_samples_global, robot_offset=0):
+        self._check(self.lib.mppi_set_shard(self._h, sample_offset, num_samples_global, robot_offset))
+
+    def set_noise(self, eps):
+        """eps: [n_robots][T-1][K][U] float32 standard normals, or None for the internal Philox stream."""
+        if eps is None:
+            self._check(self.lib.mppi_set_noise(self._h, None))
+            return
+        e = np.ascontiguousarray(eps, dtype=np.float32).reshape(self.n_robots, self.horizon_ - 1, self.num_samples_, self.U)
+        self._check(self.lib.mppi_set_noise(self._h, _fptr(e)))
+
+    def set_debug(self, flags):
+        self._check(self.lib.mppi_set_debug(self._h, flags))
+
+    def set_scan_mode(self, mode):
+        self._check(self.lib.mppi_set_scan_mode(self._h, mode))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.mppi_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def use_graph(self, enable=True):
+        self._check(self.lib.mppi_use_graph(self._h, int(enable)))
+
+    def comm_init(self, unique_id: bytes, rank, n_ranks):
+        buf = C.create_string_buffer(unique_id, _capi.COMM_ID_BYTES)
+        self._check(self.lib.mppi_comm_init(self._h, buf, rank, n_ranks))
+
+    # -- the cycle --------------------------------------------------------------------------------------
+    def solve(self, state=None, dt=None):
+        """sampling(); predict_States(); calc_Weights(); determine_OptimalSolution();  (DD:352-358)
+        Returns optimal_solution ([T-1][U] for one robot, else [R][T-1][U])."""
+        if state is not None:
+            self.current_state[...] = np.asarray(state, dtype=np.float64).reshape(self.n_robots, self.S)
+        if dt is not None:
+            self.dt_ = float(dt)
+        self._check(self.lib.mppi_solve(self._h, _dptr(self.current_state), self.dt_, _dptr(self.optimal_solution)))
+        return self.optimal_solution[0] if self.n_robots == 1 else self.optimal_solution
+
+    def upload(self, state=None, dt=None, with_nominal=True):
+        if state is not None:
+            self.current_state[...] = np.asarray(state, dtype=np.float64).reshape(self.n_robots, self.S)
+        if dt is not None:
+            self.dt_ = float(dt)
+        nom = _dptr(self.optimal_solution) if with_nominal else None
+        self._check(self.lib.mppi_upload(self._h, _dptr(self.current_state), self.dt_, nom))
+
+    def enqueue(self):
+        self._check(self.lib.mppi_enqueue(self._h))
+
+    def download(self):
+        self._check(self.lib.mppi_download(self._h, _dptr(self.optimal_solution)))
+        return self.optimal_solution[0] if self.n_robots == 1 else self.optimal_solution
+
+    def synchronize(self):
+        self._check(self.lib.mppi_synchronize(self._h))
+
+    # -- outputs beyond the controls ----------------------------------------------------------------------
+    def costs(self, robot=0):
+        out = np.empty(self.num_samples_, dtype=np.float32)
+        self._check(self.lib.mppi_get_costs(self._h, robot, _fptr(out)))
+        return out
+
+    def weights(self, robot=0):
+        out = np.empty(self.num_samples_, dtype=np.float32)
+        self._check(self.lib.mppi_get_weights(self._h, robot, _fptr(out)))
+        return out
+
+    def nearest(self, robot=0):
+        out = np.empty((self.num_samples_, self.horizon_), dtype=np.int32)
+        self._check(self.lib.mppi_get_nearest(self._h, robot, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def noise(self, robot=0):
+        out = np.empty((self.horizon_ - 1, self.num_samples_, self.U), dtype=np.float32)
+        self._check(self.lib.mppi_get_noise(self._h, robot, _fptr(out)))
+        return out
+
+    def window(self, robot=0):
+        out = np.empty((self.horizon_, 3), dtype=np.float64)
+        idx = C.c_int(0)
+        self._check(self.lib.mppi_get_window(self._h, robot, _dptr(out), C.byref(idx)))
+        return out, idx.value
+
+    def stats(self, robot=0):
+        out = np.empty(3, dtype=np.float64)
+        self._check(self.lib.mppi_get_stats(self._h, robot, _dptr(out)))
+        return dict(c_min=out[0], sum_w=out[1], ess=out[2])
+
+    def record(self, robot=0):
+        """This rank's partial {c_min, sum w, sum w^2, 0, N[(T-1)*U]} of the last solve (what the collective exchanges)."""
+        out = np.empty(4 + (self.horizon_ - 1) * self.U, dtype=np.float32)
+        self._check(self.lib.mppi_get_record(self._h, robot, _fptr(out)))
+        return out
+
+    def time_kernels(self, n_iters=5):
+        """Average device ms per kernel: noise, rollout_cost, weights, weighted_controls, finalize, merge, total."""
+        ms = np.zeros(7, dtype=np.float32)
+        self._check(self.lib.mppi_time_kernels(self._h, int(n_iters), _fptr(ms)))
+        names = ("noise", "rollout_cost", "weights", "weighted_controls", "finalize", "merge", "total")
+        return dict(zip(names, (float(v) for v in ms)))
+
+    def launch_count(self):
+        return self.lib.mppi_last_launch_count(self._h)
+
+    # first control of the horizon = what publish_CmdVel sends (DD:250-251)
+    def cmd_vel(self, robot=0):
+        return float(self.optimal_solution[robot, 0, 0]), float(self.optimal_solution[robot, 0, 1])
+
+
+class DiffDriveMPPI(_MPPIBase):
+    """class DiffDriveMPPI (diff_drive_mppi.h:52): unicycle, controls (v, w)."""
+    MODEL = "diff_drive"
+
+
+class SteeringDiffDriveMPPI(_MPPIBase):
+    """class SteeringDiffDriveMPPI (steering_diff_drive_mppi.h:56): controls (v, w, steer)."""
+    MODEL = "steering"
+
+
+class FullBodyMPPI(_MPPIBase):
+    """class FullBodyMPPI (full_body_mppi.h:68): controls (v, w, direction, roll_v, pitch_v), ZMP cost."""
+    MODEL = "full_body"
+
+
+CONTROLLERS = {"diff_drive": DiffDriveMPPI, "steering": SteeringDiffDriveMPPI, "full_body": FullBodyMPPI}
+
+
+def comm_unique_id():
+    lib = _capi.load()
+    buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+    rc = lib.mppi_comm_get_unique_id(buf)
+    if rc != 0:
+        raise _capi.MppiError(rc, lib.mppi_last_error(None).decode())
+    return buf.raw
+
+
+def merge_partials(partials, lambda_):
+    """Host merge of per-rank records [G][4+n] -> (u[n], stats) -- same arithmetic as the device merge kernel."""
+    lib = _capi.load()
+    p = np.ascontiguousarray(partials, dtype=np.float32)
+    G, rec = p.shape
+    n = rec - 4
+    u = np.empty(n, dtype=np.float32)
+    st = np.empty(3, dtype=np.float64)
+    rc = lib.mppi_merge_partials(_fptr(p), G, n, float(lambda_), _fptr(u), _dptr(st))
+    if rc != 0:
+        raise _capi.MppiError(rc, "mppi_merge_partials")
+    return u, dict(c_min=st[0], sum_w=st[1], ess=st[2])
+
+
+def calc_ref_path(path_xy, px, py, v_ref, dt, resolution, horizon):
+    lib = _capi.load()
+    xy = np.ascontiguousarray(path_xy, dtype=np.float64).reshape(-1, 2)
+    win = np.empty((horizon, 3), dtype=np.float64)
+    idx = C.c_int(0)
+    rc = lib.mppi_calc_ref_path(_dptr(xy), xy.shape[0], px, py, v_ref, dt, resolution, horizon, _dptr(win), C.byref(idx))
+    if rc != 0:
+        raise _capi.MppiError(rc, "mppi_calc_ref_path")
+    return win, idx.value
+
+
+def philox4x32_10(counter, key):
+    lib = _capi.load()
+    c = (C.c_uint32 * 4)(*counter)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib.mppi_philox4x32_10(c, k, o)
+    return [int(v) for v in o]

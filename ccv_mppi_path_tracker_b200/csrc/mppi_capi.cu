@@ -1,0 +1,731 @@
+// mppi_capi.cu -- implementation of the C ABI declared in include/mppi_b200.h.
+// Host side of one control cycle: window construction in double (get_CurrentIndex + calc_RefPath, DD:126-181),
+// one pinned staging block -> one H2D copy, the kernel sequence K1..K6 (optionally replayed from a CUDA graph),
+// one D2H copy.  No CPU fallback: without a usable CUDA device every compute entry point returns MPPI_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mppi_b200.h"
+#include "mppi_host.h"
+#include "mppi_kernels.h"
+#include "philox.h"
+
+using namespace mppi;
+
+// ---- minimal NCCL surface, resolved at run time with dlopen so that single-GPU users need no NCCL ----------
+namespace {
+struct NcclUniqueId {
+  char internal[MPPI_COMM_ID_BYTES];
+};
+typedef int (*nccl_get_unique_id_fn)(NcclUniqueId *);
+typedef int (*nccl_comm_init_rank_fn)(void **, int, NcclUniqueId, int);
+typedef int (*nccl_all_gather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_comm_destroy_fn)(void *);
+typedef const char *(*nccl_get_error_string_fn)(int);
+constexpr int kNcclFloat = 7;
+
+struct NcclApi {
+  void *lib = nullptr;
+  nccl_get_unique_id_fn get_unique_id = nullptr;
+  nccl_comm_init_rank_fn comm_init_rank = nullptr;
+  nccl_all_gather_fn all_gather = nullptr;
+  nccl_comm_destroy_fn comm_destroy = nullptr;
+  nccl_get_error_string_fn get_error_string = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+      return false;
+    }
+    get_unique_id = (nccl_get_unique_id_fn)dlsym(lib, "ncclGetUniqueId");
+    comm_init_rank = (nccl_comm_init_rank_fn)dlsym(lib, "ncclCommInitRank");
+    all_gather = (nccl_all_gather_fn)dlsym(lib, "ncclAllGather");
+    comm_destroy = (nccl_comm_destroy_fn)dlsym(lib, "ncclCommDestroy");
+    get_error_string = (nccl_get_error_string_fn)dlsym(lib, "ncclGetErrorString");
+    if (!get_unique_id || !comm_init_rank || !all_gather || !comm_destroy) {
+      err = "libnccl is missing a required symbol";
+      lib = nullptr;
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+thread_local std::string g_create_error;
+}  // namespace
+
+struct mppi_handle_s {
+  int model = 0, K = 0, T = 0, U = 0, S = 0, R = 0, device = 0;
+  mppi_params params;
+  DeviceState d;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t staged = nullptr;  // H2D of the staging block has completed
+  bool staged_pending = false;
+  // one pinned staging block mirroring d_in: header | windows | states | nominals
+  char *h_in = nullptr, *d_in = nullptr;
+  size_t in_bytes = 0, nominal_off = 0;
+  float *h_out = nullptr, *d_out = nullptr;
+  size_t out_bytes = 0;
+  // host-side per-robot inputs
+  std::vector<std::vector<double>> path;
+  std::vector<char> window_fixed;
+  std::vector<double> window;  // [R][T][3]
+  std::vector<int> cur_index;
+  bool have_inputs = false, have_nominal = false;
+  bool external_noise = false;
+  int debug_flags = 0, scan_mode = MPPI_SCAN_AUTO;
+  uint64_t seed = 0x5EED0000ull;
+  int64_t sample_offset = 0, k_global = 0;
+  int robot_offset = 0;
+  // graphs
+  bool use_graph = false;
+  cudaGraphExec_t exec_kernels = nullptr, exec_solve = nullptr;
+  int launch_count = 0;
+  // collective
+  void *comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  std::string err;
+};
+
+namespace {
+
+int fail(mppi_handle h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+#define CU_TRY(h, expr)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(h, MPPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool params_valid(const mppi_params *p) {
+  return p && p->lambda > 0.0 && p->resolution > 0.0 && p->control_noise >= 0.0;
+}
+
+void invalidate_graphs(mppi_handle h) {
+  if (h->exec_kernels) cudaGraphExecDestroy(h->exec_kernels);
+  if (h->exec_solve) cudaGraphExecDestroy(h->exec_solve);
+  h->exec_kernels = h->exec_solve = nullptr;
+}
+
+void fill_header(mppi_handle h, double dt) {
+  SolveHeader *hd = reinterpret_cast<SolveHeader *>(h->h_in);
+  hd->P = make_solve_params(h->model, h->T, h->params, dt);
+  hd->inv_lambda = (float)(1.0 / h->params.lambda);
+  hd->key0 = (uint32_t)h->seed;
+  hd->key1 = (uint32_t)(h->seed >> 32);
+  hd->robot_offset = (uint32_t)h->robot_offset;
+  hd->q_offset = (uint32_t)(h->sample_offset / 4);
+}
+
+// the kernel sequence of one solve on stream s (also what gets captured into the graph)
+int issue_kernels(mppi_handle h, cudaStream_t s) {
+  const DeviceState &d = h->d;
+  int n = 0;
+  if (h->external_noise) CU_TRY(h, launch_reset_cmin(d, s));
+  else CU_TRY(h, launch_noise(d, s));
+  ++n;
+  const bool want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && d.nearest;
+  int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
+  if (want_nearest) scan = MPPI_SCAN_LITERAL;  // the literal kernel is the one that records argmin indices
+  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, s));
+  ++n;
+  CU_TRY(h, launch_weights(d, s));
+  ++n;
+  CU_TRY(h, launch_weighted_controls(d, s));
+  ++n;
+  CU_TRY(h, launch_finalize(d, s));
+  ++n;
+  if (h->n_ranks > 1) {
+    int rc = g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s);
+    if (rc != 0)
+      return fail(h, MPPI_ERR_NCCL,
+                  std::string("ncclAllGather: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "?"));
+    ++n;
+  }
+  CU_TRY(h, launch_merge(d, s));
+  ++n;
+  h->launch_count = n;
+  return MPPI_OK;
+}
+
+int wait_staging_free(mppi_handle h) {
+  if (h->staged_pending) {
+    CU_TRY(h, cudaEventSynchronize(h->staged));
+    h->staged_pending = false;
+  }
+  return MPPI_OK;
+}
+
+// host part of the cycle: windows (double), header, robot-centred FP32 inputs into the pinned block
+int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_nominal) {
+  if (!state || !(dt > 0.0)) return fail(h, MPPI_ERR_INVALID, "state must be non-NULL and dt > 0");
+  int rc = wait_staging_free(h);
+  if (rc) return rc;
+  fill_header(h, dt);
+  const DeviceState &d = h->d;
+  float *win = reinterpret_cast<float *>(h->h_in + kHeaderBytes);
+  float *st = win + (size_t)d.R * d.win_stride;
+  float *nom = reinterpret_cast<float *>(h->h_in + h->nominal_off);
+  for (int r = 0; r < h->R; ++r) {
+    const double *s = state + (size_t)r * h->S;
+    double *w = h->window.data() + (size_t)r * h->T * 3;
+    if (!h->window_fixed[r]) {
+      if (h->path[r].empty()) return fail(h, MPPI_ERR_STATE, "no path or window set for robot " + std::to_string(r));
+      h->cur_index[r] = calc_ref_path(h->path[r].data(), (int)(h->path[r].size() / 2), s[0], s[1], h->params.v_ref,
+                                      dt, h->params.resolution, h->T, w);
+    }
+    window_to_robot_frame(w, h->T, s[0], s[1], win + (size_t)r * d.win_stride);
+    state_to_robot_frame(h->model, s, w[2], st + (size_t)r * 8);
+  }
+  if (u_nominal) {
+    const size_t n = (size_t)h->R * d.planes;
+    for (size_t k = 0; k < n; ++k) nom[k] = (float)u_nominal[k];
+  }
+  return MPPI_OK;
+}
+
+int capture(mppi_handle h, bool with_copies, cudaGraphExec_t *out) {
+  cudaGraph_t g = nullptr;
+  CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = MPPI_OK;
+  if (with_copies) {
+    cudaError_t e = cudaMemcpyAsync(h->d_in, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == MPPI_OK) rc = issue_kernels(h, h->stream);
+  if (rc == MPPI_OK && with_copies) {
+    cudaError_t e = cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  if (rc != MPPI_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  CU_TRY(h, e);
+  e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  CU_TRY(h, e);
+  return MPPI_OK;
+}
+
+void copy_out(mppi_handle h, double *u_nominal) {
+  const size_t n = (size_t)h->R * h->d.planes;
+  for (size_t k = 0; k < n; ++k) u_nominal[k] = (double)h->h_out[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+int mppi_abi_version(void) { return MPPI_B200_ABI_VERSION; }
+
+const char *mppi_last_error(mppi_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_samples, int horizon, int n_robots,
+                int device) {
+  if (!out) return fail(nullptr, MPPI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (model < 0 || model > 2) return fail(nullptr, MPPI_ERR_INVALID, "unknown model");
+  if (!params_valid(params)) return fail(nullptr, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0");
+  if (num_samples < 1 || horizon < 2 || horizon > 4096 || n_robots < 1 || n_robots > 65535)
+    return fail(nullptr, MPPI_ERR_INVALID, "need num_samples >= 1, 2 <= horizon <= 4096, 1 <= n_robots <= 65535");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, MPPI_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= ndev) return fail(nullptr, MPPI_ERR_INVALID, "device ordinal out of range");
+  mppi_handle h = new (std::nothrow) mppi_handle_s();
+  if (!h) return fail(nullptr, MPPI_ERR_ALLOC, "out of host memory");
+  h->model = model;
+  h->K = num_samples;
+  h->T = horizon;
+  h->U = num_controls(model);
+  h->S = num_states(model);
+  h->R = n_robots;
+  h->device = device;
+  h->params = *params;
+  h->k_global = num_samples;
+  DeviceState &d = h->d;
+  d.model = model;
+  d.T = horizon;
+  d.U = h->U;
+  d.K = num_samples;
+  d.Kp = (int)align_up((size_t)num_samples, 4);
+  d.R = n_robots;
+  d.planes = (horizon - 1) * h->U;
+  d.win_stride = (int)align_up((size_t)2 * horizon, 4);
+  d.rec_stride = (int)align_up((size_t)4 + d.planes, 4);
+  d.nb3 = (num_samples + kWeightBlock * 4 - 1) / (kWeightBlock * 4);
+  d.nchunk = (d.Kp + kReduceChunk - 1) / kReduceChunk;
+  d.n_ranks = 1;
+  if (d.planes > 65535) {
+    delete h;
+    return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");
+  }
+
+  auto bail = [&](int code, const std::string &msg) {
+    std::string m = msg;
+    mppi_destroy(h);
+    return fail(nullptr, code, m);
+  };
+#define CU_NEW(expr)                                                                   \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) return bail(MPPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+  CU_NEW(cudaSetDevice(device));
+  CU_NEW(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CU_NEW(cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming));
+
+  const size_t win_bytes = sizeof(float) * (size_t)d.R * d.win_stride;
+  const size_t st_bytes = sizeof(float) * (size_t)d.R * 8;
+  const size_t nom_bytes = sizeof(float) * (size_t)d.R * d.planes;
+  h->nominal_off = align_up(kHeaderBytes + win_bytes + st_bytes, 16);
+  h->in_bytes = align_up(h->nominal_off + nom_bytes, 16);
+  h->out_bytes = sizeof(float) * ((size_t)d.R * d.planes + (size_t)d.R * 4);
+  CU_NEW(cudaMallocHost((void **)&h->h_in, h->in_bytes));
+  CU_NEW(cudaMallocHost((void **)&h->h_out, h->out_bytes));
+  memset(h->h_in, 0, h->in_bytes);
+  memset(h->h_out, 0, h->out_bytes);
+  CU_NEW(cudaMalloc((void **)&h->d_in, h->in_bytes));
+  CU_NEW(cudaMemset(h->d_in, 0, h->in_bytes));
+  CU_NEW(cudaMalloc((void **)&h->d_out, h->out_bytes));
+  CU_NEW(cudaMemset(h->d_out, 0, h->out_bytes));
+  d.hdr = reinterpret_cast<SolveHeader *>(h->d_in);
+  d.window = reinterpret_cast<float *>(h->d_in + kHeaderBytes);
+  d.state = d.window + (size_t)d.R * d.win_stride;
+  d.nominal = reinterpret_cast<float *>(h->d_in + h->nominal_off);
+  d.u_new = h->d_out;
+  d.stats = h->d_out + (size_t)d.R * d.planes;
+  CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
+  CU_NEW(cudaMalloc((void **)&d.cost, sizeof(float) * (size_t)d.R * d.K));
+  CU_NEW(cudaMalloc((void **)&d.weight, sizeof(float) * (size_t)d.R * d.K));
+  CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * d.nb3 * 2));
+  CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.planes * d.nchunk));
+  CU_NEW(cudaMalloc((void **)&d.record, sizeof(float) * (size_t)d.R * d.rec_stride));
+  CU_NEW(cudaMalloc((void **)&d.cmin, sizeof(unsigned int) * (size_t)d.R));
+  CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
+  CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
+  CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
+  d.gathered = d.record;
+#undef CU_NEW
+  h->path.resize(n_robots);
+  h->window_fixed.assign(n_robots, 0);
+  h->window.assign((size_t)n_robots * horizon * 3, 0.0);
+  h->cur_index.assign(n_robots, 0);
+  *out = h;
+  return MPPI_OK;
+}
+
+int mppi_destroy(mppi_handle h) {
+  if (!h) return MPPI_OK;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  invalidate_graphs(h);
+  if (h->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(h->comm);
+  DeviceState &d = h->d;
+  if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
+  cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
+  cudaFree(d.record); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
+  cudaFree(h->d_in); cudaFree(h->d_out);
+  if (h->h_in) cudaFreeHost(h->h_in);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->staged) cudaEventDestroy(h->staged);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return MPPI_OK;
+}
+
+int mppi_set_params(mppi_handle h, const mppi_params *params) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!params_valid(params)) return fail(h, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0");
+  h->params = *params;
+  return MPPI_OK;
+}
+
+int mppi_set_debug(mppi_handle h, int debug_flags) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if ((debug_flags & MPPI_DEBUG_NEAREST) && !h->d.nearest) {
+    const size_t bytes = sizeof(int) * (size_t)h->R * h->K * h->T;
+    CU_TRY(h, cudaMalloc((void **)&h->d.nearest, bytes));
+    CU_TRY(h, cudaMemset(h->d.nearest, 0xFF, bytes));
+  }
+  if (debug_flags != h->debug_flags) invalidate_graphs(h);
+  h->debug_flags = debug_flags;
+  return MPPI_OK;
+}
+
+int mppi_set_scan_mode(mppi_handle h, int scan_mode) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (scan_mode < MPPI_SCAN_AUTO || scan_mode > MPPI_SCAN_PRUNED) return fail(h, MPPI_ERR_INVALID, "unknown scan mode");
+  if (scan_mode != h->scan_mode) invalidate_graphs(h);
+  h->scan_mode = scan_mode;
+  return MPPI_OK;
+}
+
+int mppi_set_path(mppi_handle h, int robot, const double *path_xy, int n_points) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || n_points < 1 || !path_xy) return fail(h, MPPI_ERR_INVALID, "bad robot index or empty path");
+  h->path[robot].assign(path_xy, path_xy + (size_t)2 * n_points);
+  h->window_fixed[robot] = 0;
+  return MPPI_OK;
+}
+
+int mppi_set_window(mppi_handle h, int robot, const double *window_xyyaw) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !window_xyyaw) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL window");
+  memcpy(h->window.data() + (size_t)robot * h->T * 3, window_xyyaw, sizeof(double) * 3 * (size_t)h->T);
+  h->window_fixed[robot] = 1;
+  h->cur_index[robot] = 0;
+  return MPPI_OK;
+}
+
+int mppi_set_seed(mppi_handle h, uint64_t seed, uint64_t first_solve_counter) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->seed = seed;
+  uint32_t c = (uint32_t)first_solve_counter;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(h->d.counter, &c, sizeof c, cudaMemcpyHostToDevice));
+  return MPPI_OK;
+}
+
+int mppi_set_shard(mppi_handle h, int64_t sample_offset, int64_t num_samples_global, int robot_offset) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (sample_offset < 0 || (sample_offset % 4) != 0 || num_samples_global < sample_offset + h->K || robot_offset < 0)
+    return fail(h, MPPI_ERR_INVALID, "sample_offset must be a non-negative multiple of 4 inside the global sample range");
+  h->sample_offset = sample_offset;
+  h->k_global = num_samples_global;
+  h->robot_offset = robot_offset;
+  return MPPI_OK;
+}
+
+int mppi_set_noise(mppi_handle h, const float *eps) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  const bool ext = eps != nullptr;
+  if (ext != h->external_noise) invalidate_graphs(h);
+  h->external_noise = ext;
+  if (!ext) return MPPI_OK;
+  const DeviceState &d = h->d;
+  const int K = h->K, U = h->U, steps = h->T - 1;
+  std::vector<float> phys((size_t)d.R * d.planes * d.Kp, 0.f);
+  for (int r = 0; r < d.R; ++r)
+    for (int t = 0; t < steps; ++t)
+      for (int i = 0; i < K; ++i)
+        for (int u = 0; u < U; ++u)
+          phys[((size_t)r * d.planes + (size_t)t * U + u) * d.Kp + i] = eps[(((size_t)r * steps + t) * K + i) * U + u];
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(d.eps, phys.data(), sizeof(float) * phys.size(), cudaMemcpyHostToDevice));
+  return MPPI_OK;
+}
+
+int mppi_set_stream(mppi_handle h, void *cuda_stream) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  invalidate_graphs(h);
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return MPPI_OK;
+}
+
+int mppi_use_graph(mppi_handle h, int enable) {
+  if (!h) return MPPI_ERR_INVALID;
+  h->use_graph = enable != 0;
+  if (!enable) invalidate_graphs(h);
+  return MPPI_OK;
+}
+
+int mppi_upload(mppi_handle h, const double *state, double dt, const double *u_nominal) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  int rc = stage_inputs(h, state, dt, u_nominal);
+  if (rc) return rc;
+  const size_t bytes = u_nominal ? h->in_bytes : h->nominal_off;
+  CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaEventRecord(h->staged, h->stream));
+  h->staged_pending = true;
+  h->have_inputs = true;
+  if (u_nominal) h->have_nominal = true;
+  return MPPI_OK;
+}
+
+int mppi_enqueue(mppi_handle h) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!h->have_inputs) return fail(h, MPPI_ERR_STATE, "mppi_enqueue before mppi_upload");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (h->use_graph && h->n_ranks == 1) {
+    if (!h->exec_kernels) {
+      int rc = capture(h, false, &h->exec_kernels);
+      if (rc) return rc;
+    }
+    CU_TRY(h, cudaGraphLaunch(h->exec_kernels, h->stream));
+    return MPPI_OK;
+  }
+  return issue_kernels(h, h->stream);
+}
+
+int mppi_download(mppi_handle h, double *u_nominal) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!u_nominal) return fail(h, MPPI_ERR_INVALID, "u_nominal is NULL");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->staged_pending = false;
+  copy_out(h, u_nominal);
+  return MPPI_OK;
+}
+
+int mppi_synchronize(mppi_handle h) {
+  if (!h) return MPPI_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->staged_pending = false;
+  return MPPI_OK;
+}
+
+int mppi_solve(mppi_handle h, const double *state, double dt, double *u_nominal) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!u_nominal) return fail(h, MPPI_ERR_INVALID, "u_nominal is NULL");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (h->use_graph && h->n_ranks == 1) {
+    int rc = stage_inputs(h, state, dt, u_nominal);
+    if (rc) return rc;
+    if (!h->exec_solve) {
+      rc = capture(h, true, &h->exec_solve);
+      if (rc) return rc;
+    }
+    CU_TRY(h, cudaGraphLaunch(h->exec_solve, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_inputs = h->have_nominal = true;
+    copy_out(h, u_nominal);
+    return MPPI_OK;
+  }
+  int rc = mppi_upload(h, state, dt, u_nominal);
+  if (rc) return rc;
+  rc = mppi_enqueue(h);
+  if (rc) return rc;
+  return mppi_download(h, u_nominal);
+}
+
+int mppi_get_costs(mppi_handle h, int robot, float *cost) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !cost) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(cost, h->d.cost + (size_t)robot * h->K, sizeof(float) * (size_t)h->K, cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_weights(mppi_handle h, int robot, float *weights) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !weights) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(weights, h->d.weight + (size_t)robot * h->K, sizeof(float) * (size_t)h->K, cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_nearest(mppi_handle h, int robot, int32_t *nearest) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !nearest) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  if (!(h->debug_flags & MPPI_DEBUG_NEAREST) || !h->d.nearest)
+    return fail(h, MPPI_ERR_STATE, "mppi_get_nearest needs mppi_set_debug(MPPI_DEBUG_NEAREST) before the solve");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)h->K * h->T;
+  CU_TRY(h, cudaMemcpy(nearest, h->d.nearest + (size_t)robot * n, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_noise(mppi_handle h, int robot, float *eps) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !eps) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const DeviceState &d = h->d;
+  std::vector<float> phys((size_t)d.planes * d.Kp);
+  CU_TRY(h, cudaMemcpy(phys.data(), d.eps + (size_t)robot * d.planes * d.Kp, sizeof(float) * phys.size(),
+                       cudaMemcpyDeviceToHost));
+  const int K = h->K, U = h->U, steps = h->T - 1;
+  for (int t = 0; t < steps; ++t)
+    for (int i = 0; i < K; ++i)
+      for (int u = 0; u < U; ++u) eps[((size_t)t * K + i) * U + u] = phys[((size_t)t * U + u) * d.Kp + i];
+  return MPPI_OK;
+}
+
+int mppi_get_window(mppi_handle h, int robot, double *window_xyyaw, int *current_index) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R) return fail(h, MPPI_ERR_INVALID, "bad robot index");
+  if (window_xyyaw) memcpy(window_xyyaw, h->window.data() + (size_t)robot * h->T * 3, sizeof(double) * 3 * (size_t)h->T);
+  if (current_index) *current_index = h->cur_index[robot];
+  return MPPI_OK;
+}
+
+int mppi_get_stats(mppi_handle h, int robot, double *stats) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !stats) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  float s[4];
+  CU_TRY(h, cudaMemcpy(s, h->d.stats + (size_t)robot * 4, sizeof s, cudaMemcpyDeviceToHost));
+  stats[0] = s[0];
+  stats[1] = s[1];
+  stats[2] = s[2];
+  return MPPI_OK;
+}
+
+int mppi_get_record(mppi_handle h, int robot, float *record) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !record) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(record, h->d.record + (size_t)robot * h->d.rec_stride, sizeof(float) * (4 + (size_t)h->d.planes),
+                       cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int *num_controls_out, int *n_robots) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (model) *model = h->model;
+  if (num_samples) *num_samples = h->K;
+  if (horizon) *horizon = h->T;
+  if (num_controls_out) *num_controls_out = h->U;
+  if (n_robots) *n_robots = h->R;
+  return MPPI_OK;
+}
+
+int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (n_iters < 1 || !ms) return fail(h, MPPI_ERR_INVALID, "n_iters >= 1 and ms != NULL required");
+  if (!h->have_inputs) return fail(h, MPPI_ERR_STATE, "mppi_time_kernels before mppi_upload");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaEvent_t ev[8];
+  for (auto &e : ev) CU_TRY(h, cudaEventCreate(&e));
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const DeviceState &d = h->d;
+  cudaStream_t s = h->stream;
+  const bool want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && d.nearest;
+  int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
+  if (want_nearest) scan = MPPI_SCAN_LITERAL;
+  int rc = MPPI_OK;
+  for (int it = 0; it <= n_iters && rc == MPPI_OK; ++it) {
+    cudaEventRecord(ev[0], s);
+    if (h->external_noise) launch_reset_cmin(d, s); else launch_noise(d, s);
+    cudaEventRecord(ev[1], s);
+    launch_rollout_cost(d, scan, want_nearest, s);
+    cudaEventRecord(ev[2], s);
+    launch_weights(d, s);
+    cudaEventRecord(ev[3], s);
+    launch_weighted_controls(d, s);
+    cudaEventRecord(ev[4], s);
+    launch_finalize(d, s);
+    cudaEventRecord(ev[5], s);
+    if (h->n_ranks > 1 &&
+        g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
+      rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
+    launch_merge(d, s);
+    cudaEventRecord(ev[6], s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
+    if (it == 0 || rc != MPPI_OK) continue;  // warm-up
+    for (int k = 0; k < 6; ++k) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+      acc[k] += t;
+    }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ev[0], ev[6]);
+    acc[6] += t;
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  for (int k = 0; k < 7; ++k) ms[k] = (float)(acc[k] / n_iters);
+  return rc;
+}
+
+int mppi_last_launch_count(mppi_handle h) { return h ? h->launch_count : 0; }
+
+int mppi_comm_get_unique_id(void *id_out) {
+  if (!id_out) return MPPI_ERR_INVALID;
+  if (!g_nccl.load()) return fail(nullptr, MPPI_ERR_NCCL, g_nccl.err);
+  NcclUniqueId id;
+  int rc = g_nccl.get_unique_id(&id);
+  if (rc != 0) return fail(nullptr, MPPI_ERR_NCCL, "ncclGetUniqueId failed");
+  memcpy(id_out, &id, sizeof id);
+  return MPPI_OK;
+}
+
+int mppi_comm_init(mppi_handle h, const void *id, int rank, int n_ranks) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, MPPI_ERR_INVALID, "bad rank / n_ranks / id");
+  if (h->comm) return fail(h, MPPI_ERR_STATE, "communicator already initialised");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (n_ranks == 1) return MPPI_OK;
+  if (!g_nccl.load()) return fail(h, MPPI_ERR_NCCL, g_nccl.err);
+  NcclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  int rc = g_nccl.comm_init_rank(&h->comm, n_ranks, uid, rank);
+  if (rc != 0)
+    return fail(h, MPPI_ERR_NCCL,
+                std::string("ncclCommInitRank: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "?"));
+  CU_TRY(h, cudaMalloc((void **)&h->d.gathered, sizeof(float) * (size_t)n_ranks * h->d.R * h->d.rec_stride));
+  h->d.n_ranks = n_ranks;
+  h->n_ranks = n_ranks;
+  h->rank = rank;
+  invalidate_graphs(h);
+  return MPPI_OK;
+}
+
+int mppi_merge_partials(const float *partials, int n_ranks, int n, double lambda, float *u_out, double *stats) {
+  if (!partials || n_ranks < 1 || n < 0 || !(lambda > 0.0) || (n > 0 && !u_out)) return MPPI_ERR_INVALID;
+  // same record layout as the device: {m, S, Q, -, N[n]} with stride 4 + n
+  const size_t stride = (size_t)4 + n;
+  const float inv_lambda = (float)(1.0 / lambda);
+  const float m = merge_min(partials, n_ranks, stride);
+  float S, Q;
+  merge_sums(partials, n_ranks, stride, m, inv_lambda, S, Q);
+  for (int p = 0; p < n; ++p) u_out[p] = merge_numerator(partials, n_ranks, stride, m, inv_lambda, p) / S;
+  if (stats) {
+    stats[0] = m;
+    stats[1] = S;
+    stats[2] = (double)S * S / Q;
+  }
+  return MPPI_OK;
+}
+
+int mppi_calc_ref_path(const double *path_xy, int n_points, double px, double py, double v_ref, double dt,
+                       double resolution, int horizon, double *window_xyyaw, int *current_index_out) {
+  if (!path_xy || n_points < 1 || horizon < 1 || !window_xyyaw || !(resolution > 0.0)) return MPPI_ERR_INVALID;
+  int cur = calc_ref_path(path_xy, n_points, px, py, v_ref, dt, resolution, horizon, window_xyyaw);
+  if (current_index_out) *current_index_out = cur;
+  return MPPI_OK;
+}
+
+void mppi_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+  Philox4 r = philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1]);
+  for (int k = 0; k < 4; ++k) out[k] = r.v[k];
+}
+
+}  // extern "C"

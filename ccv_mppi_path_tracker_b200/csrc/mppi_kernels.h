@@ -1,0 +1,117 @@
+// mppi_kernels.h -- device-side data layout and kernel launchers of the MPPI core (internal, not the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mppi_math.h"
+
+namespace mppi {
+
+// Everything that can change from one solve to the next lives in device memory (not in kernel arguments), so
+// a captured CUDA graph of the solve can be replayed unchanged: the host rewrites the pinned copy of this
+// header and the graph's H2D node carries it over.
+struct SolveHeader {
+  SolveParams P;
+  float inv_lambda;
+  uint32_t key0, key1;    // Philox key = 64-bit seed
+  uint32_t robot_offset;  // global index of robot 0 of this handle
+  uint32_t q_offset;      // global sample offset of this shard / 4
+  uint32_t pad[3];
+};
+
+// HBM layout owned by one handle.  R robots, K samples (this shard), T horizon, U controls, P = (T-1)*U planes.
+//   inbuf    one allocation, one H2D copy per solve:
+//     hdr      SolveHeader (padded to 256 B)
+//     window   [R][WS]   WS floats: T x {x_ref - x0, y_ref - y0} (robot-centred frame, FP32), padded to 16 B
+//     state    [R][8]    {0, 0, yaw, roll, pitch, yaw_ref[0], -, -}
+//     nominal  [R][P]    warm start u*; the merge kernel overwrites it in place with the new controls
+//   eps      [R][P][Kp]  standard normals, plane-major: one warp reads 32 consecutive samples of one (t,u)
+//                        plane (128 B coalesced); Kp = K rounded up to 4 (float4 stores of the generator)
+//   cost     [R][K]      per-sample cost;  weight [R][K] exp(-(c - c_min)/lambda)
+//   cmin     [R]         ordered-uint encoding of the minimum cost (atomicMin target)
+//   wpart    [R][NB3][2] per-block partial (sum w, sum w^2) of the weight kernel (fixed-order final sum)
+//   npart    [R][P][NC]  per-chunk partial numerators of the weighted control reduction
+//   record   [R][REC]    REC = 4 + P floats: {c_min, sum w, sum w^2, -, N[P]} -- the exchanged partial
+//   gathered [G][R][REC] all ranks' records (G = 1 when not sharded: aliased to record)
+//   outbuf   one allocation, one D2H copy per solve:  u_new [R][P], stats [R][4] = {c_min, sum w, ESS, -}
+//   nearest  [R][K][T]   int32, debug only
+//   counter  [1]         solve counter of the Philox stream, advanced on the device by the merge kernel
+struct DeviceState {
+  int model = 0, T = 0, U = 0;
+  int K = 0, Kp = 0, R = 0, planes = 0, win_stride = 0, rec_stride = 0;
+  int nb3 = 0, nchunk = 0, n_ranks = 1;
+  SolveHeader *hdr = nullptr;
+  float *window = nullptr, *state = nullptr, *nominal = nullptr;
+  float *eps = nullptr, *cost = nullptr, *weight = nullptr, *wpart = nullptr, *npart = nullptr;
+  float *record = nullptr, *gathered = nullptr;
+  float *u_new = nullptr, *stats = nullptr;
+  unsigned int *cmin = nullptr;
+  uint32_t *counter = nullptr;
+  int *nearest = nullptr;
+};
+
+constexpr int kHeaderBytes = 256;
+constexpr int kWeightBlock = 256;   // threads of the weight kernel, 4 samples per thread
+constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
+constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
+static_assert(sizeof(SolveHeader) <= kHeaderBytes, "SolveHeader must fit its slot");
+
+// K1  Philox4x32-10 + Box-Muller -> eps (float4 stores).  Also resets cmin.
+cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
+// used instead of K1 when the caller supplied the noise tensor (mppi_set_noise)
+cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
+// K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
+cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s);
+// K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums
+cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
+// K4  weighted control reduction partials
+cudaError_t launch_weighted_controls(const DeviceState &d, cudaStream_t s);
+// K5  fixed-order final sums -> record;  K6 merge of G records -> u_new, nominal, stats, counter++
+cudaError_t launch_finalize(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_merge(const DeviceState &d, cudaStream_t s);
+
+// ordered-uint encoding so that atomicMin(unsigned) orders floats (negative costs included)
+MPPI_HD uint32_t float_to_ordered(float f) {
+  uint32_t u = float_to_bits(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+MPPI_HD float ordered_to_float(uint32_t u) {
+  return bits_to_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// Merge of per-rank partial records, shared by the device merge kernel and mppi_merge_partials (host).
+//   rec_g = {m_g, S_g, Q_g, -, N_g[n]} with S_g = sum exp(-(c-m_g)/lambda), Q_g = sum of squares.
+//   m = min m_g;  a_g = exp(-(m_g - m)/lambda);  S = sum a_g S_g;  N = sum a_g N_g;  u = N / S.
+// Ranks are combined in rank order (deterministic).
+MPPI_HD float merge_min(const float *recs, int n_ranks, size_t rank_stride) {
+  float m = recs[0];
+  for (int g = 1; g < n_ranks; ++g) {
+    float mg = recs[(size_t)g * rank_stride];
+    m = mg < m ? mg : m;
+  }
+  return m;
+}
+MPPI_HD float merge_scale(float m_g, float m, float inv_lambda, int n_ranks) {
+  return n_ranks == 1 ? 1.f : expf(-(m_g - m) * inv_lambda);
+}
+MPPI_HD void merge_sums(const float *recs, int n_ranks, size_t rank_stride, float m, float inv_lambda, float &S,
+                        float &Q) {
+  S = 0.f;
+  Q = 0.f;
+  for (int g = 0; g < n_ranks; ++g) {
+    const float *r = recs + (size_t)g * rank_stride;
+    float a = merge_scale(r[0], m, inv_lambda, n_ranks);
+    S = fmaf(a, r[1], S);
+    Q = fmaf(a * a, r[2], Q);
+  }
+}
+MPPI_HD float merge_numerator(const float *recs, int n_ranks, size_t rank_stride, float m, float inv_lambda, int p) {
+  float N = 0.f;
+  for (int g = 0; g < n_ranks; ++g) {
+    const float *r = recs + (size_t)g * rank_stride;
+    N = fmaf(merge_scale(r[0], m, inv_lambda, n_ranks), r[4 + p], N);
+  }
+  return N;
+}
+
+}  // namespace mppi

@@ -1,0 +1,284 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Run on the B200 box: pytest -m gpu.
+
+Contract (DESIGN.md "Parity"):
+  * nearest window index per (sample, t): bit-exact GPU == FP32 twin; twin == FP64 oracle except at near-ties
+  * per-sample cost: bit-exact GPU == FP32 twin; |c_gpu - c_fp64| <= 1e-5 |c| + 1e-5
+  * new control sequence: |u_gpu - u_fp64| <= 1e-3 (u_max - u_min) per control (ESS printed beside it)
+"""
+import numpy as np
+import pytest
+
+import oracle
+from ccv_mppi_path_tracker_b200 import CONTROLLERS, _capi, params, paths
+from common import make_case
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-5
+COST_ATOL = 1e-5
+U_TOL = 1e-3  # fraction of the control range
+
+
+def _urange(case):
+    sp = case["sp"]
+    return np.array(sp["u_max"][: case["U"]]) - np.array(sp["u_min"][: case["U"]])
+
+
+def _make_ctl(case, n_robots=1, **kw):
+    ov = dict(case["overrides"])
+    ov.update(kw)
+    ctl = CONTROLLERS[case["model"]](launch=True, n_robots=n_robots, horizon=case["T"], num_samples=case["K"], **ov)
+    for r in range(n_robots):
+        ctl.set_path(case["path"], robot=r)
+    return ctl
+
+
+CONFIGS = [
+    # BASELINE.json configs at sizes the FP64 oracle finishes in seconds
+    ("diff_drive", 1000, 15),   # config 1: launch default
+    ("steering", 4096, 50),     # config 2
+    ("full_body", 2048, 100),   # config 3 shape (K reduced), tail-clamped window (T=100 on a 200-point path)
+    ("diff_drive", 4096, 100),  # config 4 shape (K reduced), T=100 window clamps at the 101-point path tail
+    ("diff_drive", 1024, 50),   # config 5 shape (one robot)
+]
+
+
+@pytest.mark.parametrize("model,K,T", CONFIGS)
+def test_external_noise_matches_twin_and_oracle(model, K, T):
+    case = make_case(model, K, T, seed=11)
+    with _make_ctl(case) as ctl:
+        ctl.set_noise(case["eps"][None])
+        ctl.set_debug(_capi.DEBUG_NEAREST)
+        ctl.optimal_solution[0] = case["u0"]
+        u_gpu = ctl.solve(case["state"], case["dt"]).copy()
+        window, cur = ctl.window()
+        cost_gpu, near_gpu = ctl.costs(), ctl.nearest()
+        st = ctl.stats()
+        # the tensor read back is the tensor we fed
+        assert np.array_equal(ctl.noise(), case["eps"])
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"],
+                                  want=("nearest", "d2"))
+    o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"])
+    assert np.array_equal(window, o["window"]) and cur == oracle.calc_ref_path(
+        case["path"], case["state"][0], case["state"][1], case["sp"]["v_ref"], case["dt"], case["sp"]["resolution"], T)[1]
+    Tc = T - 2 if model == "full_body" else T
+    # bit-exact against the FP32 twin
+    assert np.array_equal(near_gpu[:, :Tc], tw["nearest"][:, :Tc])
+    assert np.array_equal(cost_gpu.view(np.uint32), tw["cost"].view(np.uint32))
+    # FP64 oracle: indices equal except near-ties, costs / controls within tolerance
+    mism = near_gpu[:, :Tc] != o["nearest"][:, :Tc]
+    assert mism.mean() < 1e-4, f"{mism.sum()} index mismatches vs FP64"
+    assert np.all(np.abs(cost_gpu - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+    err = np.abs(u_gpu - o["u_new"]) / _urange(case)
+    print(f"{model} K={K} T={T}: idx mismatches vs fp64 {mism.sum()}, max|du|/range {err.max():.2e}, "
+          f"ESS gpu {st['ess']:.2f} fp64 {o['stats'][2]:.2f}")
+    assert err.max() <= U_TOL
+    assert abs(st["c_min"] - o["stats"][0]) <= COST_RTOL * abs(o["stats"][0]) + COST_ATOL
+    assert abs(st["ess"] - o["stats"][2]) <= 1e-2 * o["stats"][2]
+
+
+@pytest.mark.parametrize("model", ["diff_drive", "steering", "full_body"])
+def test_internal_noise_chain_matches_oracle(model):
+    """Three chained solves on the internal Philox stream (warm start not time shifted): feed the dumped tensor
+    of every solve to the FP64 oracle and compare the controls after each."""
+    K, T = 2048, 20
+    case = make_case(model, K, T)
+    with _make_ctl(case) as ctl:
+        ctl.set_seed(0x5EED0000 + 1, 0)
+        u_ref = np.zeros((T - 1, case["U"]))
+        state = case["state"].copy()
+        for it in range(3):
+            u_gpu = ctl.solve(state, case["dt"]).copy()
+            eps = ctl.noise()
+            o = oracle.solve(model, case["sp"], K, T, state, case["dt"], case["path"], eps, u_ref)
+            err = np.abs(u_gpu - o["u_new"]) / _urange(case)
+            assert err.max() <= U_TOL, (it, err.max())
+            u_ref = u_gpu  # continue the chain from the GPU's own warm start
+            state[0] += 0.1
+
+
+def test_philox_noise_tensor():
+    """K1: statistics, reproducibility, shard-independence and exact Philox counters of the noise tensor."""
+    K, T = 4096, 30
+    case = make_case("steering", K, T)
+    with _make_ctl(case) as ctl:
+        ctl.set_seed(1234, 7)
+        ctl.solve(case["state"], case["dt"])
+        e1 = ctl.noise()
+        ctl.solve(case["state"], case["dt"])
+        e2 = ctl.noise()
+        ctl.set_seed(1234, 7)
+        ctl.solve(case["state"], case["dt"])
+        e3 = ctl.noise()
+    assert np.array_equal(e1, e3) and not np.array_equal(e1, e2)
+    x = e1.astype(np.float64).ravel()
+    n = x.size
+    assert abs(x.mean()) < 5 / np.sqrt(n) and abs(x.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((x ** 4).mean() - 3) < 0.1 and np.abs(x).max() < 6.0
+    # element (t, i, u) from its counter: c0 = i // 4, c1 = t*U + u, c2 = robot, c3 = solve counter, key = seed
+    from ccv_mppi_path_tracker_b200 import philox4x32_10
+    for (t, i, u) in [(0, 0, 0), (3, 17, 2), (28, 4095, 1), (11, 2049, 0)]:
+        r = philox4x32_10([i // 4, t * 3 + u, 0, 7], [1234, 0])
+        pair = 0 if (i % 4) < 2 else 2
+        u1 = ((r[pair] >> 8) + 0.5) * 2.0 ** -24
+        ang = np.int32(np.uint32(r[pair + 1])) * (np.pi * 2.0 ** -31)
+        rad = np.sqrt(-2.0 * np.log(u1))
+        z = rad * (np.cos(ang) if (i % 2) == 0 else np.sin(ang))
+        assert abs(e1[t, i, u] - z) < 2e-5 * max(1.0, abs(z)), (t, i, u, e1[t, i, u], z)
+
+
+def test_batched_robots_equal_single_robot_solves():
+    """Config-5 shape: every robot of a batched handle gets exactly the result of its own single-robot handle."""
+    K, T, R = 512, 50, 5
+    case = make_case("diff_drive", K, T)
+    rng = np.random.default_rng(5)
+    states = np.zeros((R, 3))
+    path_sets = []
+    for r in range(R):
+        d1 = 2 * np.pi * r / R
+        pth = paths.sin_path(course_length=10.0, A1=1.0, omega1=0.25, delta1=d1, delta2=0.0, delta3=0.0)
+        j = (7 * r) % pth.shape[0]
+        states[r, :2] = pth[j] + 0.1 * rng.standard_normal(2)
+        states[r, 2] = 0.3 * rng.standard_normal()
+        path_sets.append(pth)
+    eps = rng.standard_normal((R, T - 1, K, 2)).astype(np.float32)
+    with _make_ctl(case, n_robots=R) as ctl:
+        for r in range(R):
+            ctl.set_path(path_sets[r], robot=r)
+        ctl.set_noise(eps)
+        u_b = ctl.solve(states, case["dt"]).copy()
+        cost_b = [ctl.costs(r) for r in range(R)]
+    for r in range(R):
+        with _make_ctl(case) as one:
+            one.set_path(path_sets[r])
+            one.set_noise(eps[r][None])
+            u_1 = one.solve(states[r], case["dt"]).copy()
+            assert np.array_equal(one.costs().view(np.uint32), cost_b[r].view(np.uint32))
+        assert np.array_equal(u_b[r], u_1)
+        o = oracle.solve("diff_drive", case["sp"], K, T, states[r], case["dt"], path_sets[r], eps[r], np.zeros((T - 1, 2)))
+        assert (np.abs(u_b[r] - o["u_new"]) / _urange(case)).max() <= U_TOL
+
+
+def test_sample_shards_merge_to_the_unsharded_solve():
+    """Config-4 shape on one GPU: two handles own half of the samples each (disjoint Philox sub-streams); merging
+    their partial records with mppi_merge_partials reproduces the unsharded controls."""
+    from ccv_mppi_path_tracker_b200 import merge_partials
+    K, T = 8192, 40
+    case = make_case("diff_drive", K, T)
+    with _make_ctl(case) as full:
+        full.set_seed(99, 3)
+        u_full = full.solve(case["state"], case["dt"]).copy()
+        eps_full = full.noise()
+        st_full = full.stats()
+    half = make_case("diff_drive", K // 2, T)
+    recs, eps_parts = [], []
+    for g in range(2):
+        with _make_ctl(half) as sh:
+            sh.set_seed(99, 3)
+            sh.set_shard(g * (K // 2), K, 0)
+            sh.solve(case["state"], case["dt"])
+            recs.append(sh.record())
+            eps_parts.append(sh.noise())
+    assert np.array_equal(np.concatenate(eps_parts, axis=1), eps_full)
+    u_m, st = merge_partials(np.stack(recs), case["sp"]["lambda_"])
+    err = np.abs(u_m.reshape(T - 1, 2) - u_full) / _urange(case)
+    assert err.max() < 1e-5, err.max()
+    assert abs(st["c_min"] - st_full["c_min"]) == 0 and abs(st["ess"] - st_full["ess"]) < 1e-3 * st_full["ess"]
+
+
+def test_graph_replay_equals_stream_launch():
+    case = make_case("steering", 4096, 50)
+    outs = []
+    for graph in (False, True):
+        with _make_ctl(case) as ctl:
+            ctl.set_seed(5, 0)
+            ctl.use_graph(graph)
+            us = [ctl.solve(case["state"], case["dt"]).copy() for _ in range(3)]
+            outs.append(np.stack(us))
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0][0], outs[0][1])  # the solve counter advanced inside the replayed graph
+
+
+def test_split_api_keeps_the_warm_start_on_the_device():
+    case = make_case("diff_drive", 2048, 15)
+    with _make_ctl(case) as a, _make_ctl(case) as b:
+        for c in (a, b):
+            c.set_seed(8, 0)
+        u1 = [a.solve(case["state"], case["dt"]).copy() for _ in range(3)][-1]
+        b.upload(case["state"], case["dt"], with_nominal=True)
+        for _ in range(3):
+            b.enqueue()
+        u2 = b.download().copy()
+    assert np.array_equal(u1, u2)
+
+
+@pytest.mark.parametrize("K,T", [(1, 2), (3, 3), (1001, 15), (37, 7)])
+def test_ragged_sizes(K, T):
+    for model in ("diff_drive", "steering", "full_body"):
+        case = make_case(model, K, T, seed=K + T)
+        with _make_ctl(case) as ctl:
+            ctl.set_noise(case["eps"][None])
+            ctl.set_debug(_capi.DEBUG_NEAREST)
+            ctl.optimal_solution[0] = case["u0"]
+            u_gpu = ctl.solve(case["state"], case["dt"]).copy()
+            window, _ = ctl.window()
+            tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"])
+            assert np.array_equal(ctl.costs().view(np.uint32), tw["cost"].view(np.uint32))
+        o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"])
+        assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+
+
+def test_degenerate_paths_and_far_robot():
+    """data/data.csv is a single point; a robot > 100 m from every path point hits the min_distance cap
+    (d^2 = 1e4, index -1, get_CurrentIndex returns 0)."""
+    K, T = 512, 15
+    case = make_case("diff_drive", K, T)
+    one_point = np.array([[-5.45606, -6.61448]])
+    for pth, state in ((one_point, np.array([-5.0, -6.0, 0.3])), (case["path"], np.array([500.0, -300.0, 1.0]))):
+        with _make_ctl(case) as ctl:
+            ctl.set_path(pth)
+            ctl.set_noise(case["eps"][None])
+            ctl.set_debug(_capi.DEBUG_NEAREST)
+            u_gpu = ctl.solve(state, case["dt"]).copy()
+            near = ctl.nearest()
+            cost = ctl.costs()
+        o = oracle.solve("diff_drive", case["sp"], K, T, state, case["dt"], pth, case["eps"], np.zeros((T - 1, 2)))
+        assert np.array_equal(near, o["nearest"])
+        assert np.all(np.abs(cost - o["cost"]) <= 1e-5 * np.abs(o["cost"]) + 1e-5)
+        assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+    assert (near == -1).all()
+
+
+def test_roll_off_and_steer_off_switches():
+    K, T = 1024, 20
+    for ov in (dict(roll_off=True), dict(roll_off=False, steer_off=True)):
+        case = make_case("full_body", K, T, **ov)
+        with _make_ctl(case) as ctl:
+            ctl.set_noise(case["eps"][None])
+            ctl.optimal_solution[0] = case["u0"]
+            u_gpu = ctl.solve(case["state"], case["dt"]).copy()
+            cost = ctl.costs()
+        o = oracle.solve("full_body", case["sp"], K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"])
+        assert np.all(np.abs(cost - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+        assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+        if ov.get("steer_off"):
+            assert np.all(u_gpu[:, 2] == 0.0)
+
+
+def test_error_codes():
+    case = make_case("diff_drive", 64, 5)
+    ctl = CONTROLLERS["diff_drive"](horizon=5, num_samples=64)
+    with pytest.raises(_capi.MppiError) as e:
+        ctl.solve(case["state"], 0.1)  # no path yet
+    assert e.value.code == _capi.MPPI_ERR_STATE
+    ctl.set_path(case["path"])
+    with pytest.raises(_capi.MppiError) as e:
+        ctl.solve(case["state"], 0.0)  # dt must be positive
+    assert e.value.code == _capi.MPPI_ERR_INVALID
+    with pytest.raises(_capi.MppiError):
+        ctl.nearest()  # debug tap not enabled
+    with pytest.raises(_capi.MppiError):
+        ctl.set_shard(2, 64, 0)  # offset not a multiple of 4
+    ctl.close()
+    with pytest.raises(_capi.MppiError):
+        CONTROLLERS["diff_drive"](horizon=1)
