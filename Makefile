@@ -15,8 +15,8 @@ REF       ?= /root/reference
 all: lib oracle harness
 
 lib: $(LIB)
-$(LIB): $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_capi.cu $(CSRC)/mppi_kernels.h $(CSRC)/mppi_math.h $(CSRC)/mppi_host.h $(CSRC)/philox.h include/mppi_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_capi.cu -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
+$(LIB): $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_rollout_pruned.cu $(CSRC)/mppi_device.cuh $(CSRC)/mppi_capi.cu $(CSRC)/mppi_kernels.h $(CSRC)/mppi_math.h $(CSRC)/mppi_host.h $(CSRC)/philox.h include/mppi_b200.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_rollout_pruned.cu $(CSRC)/mppi_capi.cu -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "registers|spill" $(CSRC)/ptxas.log | sort | uniq -c | sort -rn | head -40 || true
 
 harness: $(PKG)/mppi_harness

@@ -8,20 +8,10 @@
 // Compiled with -fmad=false: all FMAs are explicit (see mppi_math.h).
 #include "mppi_kernels.h"
 
+#include "mppi_device.cuh"
 #include "philox.h"
 
 namespace mppi {
-
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: noise
@@ -101,27 +91,6 @@ struct NearestSink {
   __device__ __forceinline__ void zmp(int, float, float) {}
 };
 
-// block-level min of the per-thread costs, one atomicMin per block
-__device__ __forceinline__ void block_min_to_global(float c, bool valid, unsigned int *cmin_slot, float *s_red) {
-  float v = valid ? c : INFINITY;
-  v = warp_min(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) s_red[wid] = v;
-  __syncthreads();
-  if (wid == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    float m = lane < nw ? s_red[lane] : INFINITY;
-    m = warp_min(m);
-    if (lane == 0 && m < INFINITY) atomicMin(cmin_slot, float_to_ordered(m));
-  }
-}
-
-__device__ __forceinline__ void load_params_to_shared(SolveParams *dst, const SolveHeader *hdr) {
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(&hdr->P);
-  uint32_t *d = reinterpret_cast<uint32_t *>(dst);
-  for (int k = threadIdx.x; k < (int)(sizeof(SolveParams) / 4); k += blockDim.x) d[k] = src[k];
-}
-
 template <int MODEL>
 __global__ void __launch_bounds__(128)
     rollout_cost_literal_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ eps,
@@ -157,13 +126,22 @@ __global__ void __launch_bounds__(128)
 }
 
 cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s) {
-  (void)scan_mode;
+  // scan_mode 2 = exact pruned scan (production); 1 = literal (every window point; the one that records argmin)
+  if (scan_mode == 2 && !write_nearest && pruned_scan_supported(d.T, d.planes)) return launch_rollout_cost_pruned(d, s);
   dim3 grid((d.K + 127) / 128, d.R);
   size_t smem = sizeof(float) * (2 * (size_t)d.T + d.planes);
   int *nearest = write_nearest ? d.nearest : nullptr;
 #define MPPI_LAUNCH_LITERAL(M)                                                                                   \
-  rollout_cost_literal_kernel<M><<<grid, 128, smem, s>>>(d.hdr, d.eps, d.nominal, d.window, d.state, d.cost,     \
-                                                         d.cmin, nearest, d.K, d.Kp, d.planes, d.win_stride, d.T)
+  do {                                                                                                           \
+    if (smem > 48 * 1024) {                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(rollout_cost_literal_kernel<M>,                                       \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    rollout_cost_literal_kernel<M><<<grid, 128, smem, s>>>(d.hdr, d.eps, d.nominal, d.window, d.state, d.cost,   \
+                                                           d.cmin, nearest, d.K, d.Kp, d.planes, d.win_stride,   \
+                                                           d.T);                                                 \
+  } while (0)
   switch (d.model) {
     case kDiffDrive: MPPI_LAUNCH_LITERAL(kDiffDrive); break;
     case kSteering: MPPI_LAUNCH_LITERAL(kSteering); break;

@@ -62,6 +62,9 @@ cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
 cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s);
+// K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
+cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s);
+bool pruned_scan_supported(int T, int planes);
 // K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 // K4  weighted control reduction partials

@@ -245,7 +245,11 @@ def test_degenerate_paths_and_far_robot():
         o = oracle.solve("diff_drive", case["sp"], K, T, state, case["dt"], pth, case["eps"], np.zeros((T - 1, 2)))
         assert np.array_equal(near, o["nearest"])
         assert np.all(np.abs(cost - o["cost"]) <= 1e-5 * np.abs(o["cost"]) + 1e-5)
-        assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+        # Far robot: every sample carries the same capped path cost T * path_weight * 1e4 = 1.5e6, where one FP32
+        # ulp is 0.125 -- the velocity term that separates the samples is resolved to ~0.06 / lambda in the
+        # weights, so the controls agree to ~1e-2 of the range only (FP32 regime limit, DESIGN.md "Parity").
+        tol = U_TOL if pth is one_point else 2e-2
+        assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= tol
     assert (near == -1).all()
 
 
@@ -282,3 +286,75 @@ def test_error_codes():
     ctl.close()
     with pytest.raises(_capi.MppiError):
         CONTROLLERS["diff_drive"](horizon=1)
+
+
+# ---- the production (pruned) nearest-point scan: exact, bit-identical to the literal scan ---------------------
+
+def _windows_for_pruning(T, rng):
+    """Windows that stress the pruning bounds: smooth, looping back on itself, clustered duplicates, random scatter,
+    far away (cap), and with huge coordinates."""
+    s = np.arange(T) * 0.12
+    out = {}
+    out["sine"] = np.stack([s, np.cos(2 * np.pi * 0.25 * s) - 1.0], 1)
+    ang = np.linspace(0, 4 * np.pi, T)                     # two laps of a small circle: far indices are close in space
+    out["two_laps"] = np.stack([1.5 * np.cos(ang) - 1.5, 1.5 * np.sin(ang)], 1)
+    out["hairpin"] = np.stack([np.where(s < s[T // 2], s, 2 * s[T // 2] - s), np.where(s < s[T // 2], 0.0, 0.3)], 1)
+    out["tail_clamped"] = np.stack([np.minimum(s, 3.0), np.zeros(T)], 1)   # calc_RefPath past the end of the path
+    out["scatter"] = rng.uniform(-3, 3, size=(T, 2))
+    out["far"] = out["sine"] + np.array([400.0, 300.0])
+    out["all_same"] = np.zeros((T, 2))
+    return out
+
+
+@pytest.mark.parametrize("model,K,T", [("diff_drive", 4096, 100), ("steering", 2048, 50), ("full_body", 2048, 100),
+                                       ("diff_drive", 1500, 37)])
+def test_pruned_scan_bit_identical_to_literal_and_twin(model, K, T):
+    rng = np.random.default_rng(T + K)
+    case = make_case(model, K, T, seed=3)
+    for name, xy in _windows_for_pruning(T, rng).items():
+        window = np.concatenate([xy, np.zeros((T, 1))], 1)
+        costs = {}
+        for mode in (_capi.SCAN_LITERAL, _capi.SCAN_PRUNED):
+            with _make_ctl(case) as ctl:
+                ctl.set_window(window)
+                ctl.set_noise(case["eps"][None])
+                ctl.set_scan_mode(mode)
+                ctl.optimal_solution[0] = case["u0"]
+                u = ctl.solve(case["state"], case["dt"]).copy()
+                costs[mode] = (ctl.costs(), u)
+        assert np.array_equal(costs[_capi.SCAN_LITERAL][0].view(np.uint32), costs[_capi.SCAN_PRUNED][0].view(np.uint32)), name
+        assert np.array_equal(costs[_capi.SCAN_LITERAL][1], costs[_capi.SCAN_PRUNED][1]), name
+        tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"])
+        assert np.array_equal(costs[_capi.SCAN_PRUNED][0].view(np.uint32), tw["cost"].view(np.uint32)), name
+
+
+def test_pruned_scan_fast_moving_samples():
+    """Rollouts that jump several leaves per step (v_max = 30 m/s) defeat the temporal-coherence guess; the bounds
+    must catch every such case and fall back."""
+    K, T = 4096, 100
+    case = make_case("diff_drive", K, T, seed=9, v_max=30.0, v_min=-30.0, control_noise=8.0)
+    outs = []
+    for mode in (_capi.SCAN_LITERAL, _capi.SCAN_PRUNED):
+        with _make_ctl(case) as ctl:
+            ctl.set_noise(case["eps"][None])
+            ctl.set_scan_mode(mode)
+            ctl.solve(case["state"], case["dt"])
+            outs.append(ctl.costs())
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("model,K,T", CONFIGS)
+def test_production_path_matches_oracle(model, K, T):
+    """Default configuration (AUTO scan, no debug taps, internal Philox noise): costs bit-exact against the twin,
+    controls within tolerance of the FP64 oracle fed the dumped noise."""
+    case = make_case(model, K, T, seed=21)
+    with _make_ctl(case) as ctl:
+        ctl.set_seed(0xABCDEF, 5)
+        ctl.optimal_solution[0] = case["u0"]
+        u_gpu = ctl.solve(case["state"], case["dt"]).copy()
+        eps, cost = ctl.noise(), ctl.costs()
+        window, _ = ctl.window()
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, eps, case["u0"])
+    assert np.array_equal(cost.view(np.uint32), tw["cost"].view(np.uint32))
+    o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], eps, case["u0"])
+    assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
