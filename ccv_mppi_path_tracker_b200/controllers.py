@@ -192,9 +192,9 @@ class _MPPIBase:
 
     def time_kernels(self, n_iters=5):
         """Average device ms per kernel: noise, rollout_cost, weights, weighted_controls, finalize, merge, total."""
-        ms = np.zeros(7, dtype=np.float32)
+        ms = np.zeros(8, dtype=np.float32)
         self._check(self.lib.mppi_time_kernels(self._h, int(n_iters), _fptr(ms)))
-        names = ("noise", "rollout_cost", "weights", "weighted_controls", "finalize", "merge", "total")
+        names = ("noise", "rollout_cost", "weights", "weighted_controls", "finalize", "merge", "total", "candidate_grid")
         return dict(zip(names, (float(v) for v in ms)))
 
     def launch_count(self):

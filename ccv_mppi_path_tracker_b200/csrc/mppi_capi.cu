@@ -135,6 +135,14 @@ void fill_header(mppi_handle h, double dt) {
   hd->q_offset = (uint32_t)(h->sample_offset / 4);
 }
 
+// which nearest-point scan the next solve runs: the literal kernel is the one that records argmin indices
+int effective_scan(mppi_handle h, bool *want_nearest) {
+  *want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && h->d.nearest;
+  int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
+  if (*want_nearest || !pruned_scan_supported(h->d.T, h->d.planes)) scan = MPPI_SCAN_LITERAL;
+  return scan;
+}
+
 // the kernel sequence of one solve on stream s (also what gets captured into the graph)
 int issue_kernels(mppi_handle h, cudaStream_t s) {
   const DeviceState &d = h->d;
@@ -142,9 +150,12 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
   if (h->external_noise) CU_TRY(h, launch_reset_cmin(d, s));
   else CU_TRY(h, launch_noise(d, s));
   ++n;
-  const bool want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && d.nearest;
-  int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
-  if (want_nearest) scan = MPPI_SCAN_LITERAL;  // the literal kernel is the one that records argmin indices
+  bool want_nearest;
+  const int scan = effective_scan(h, &want_nearest);
+  if (scan == MPPI_SCAN_PRUNED) {
+    CU_TRY(h, launch_candidate_grid(d, s));
+    ++n;
+  }
   CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, s));
   ++n;
   CU_TRY(h, launch_weights(d, s));
@@ -278,6 +289,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.nb3 = (num_samples + kWeightBlock * 4 - 1) / (kWeightBlock * 4);
   d.nchunk = (d.Kp + kReduceChunk - 1) / kReduceChunk;
   d.n_ranks = 1;
+  // candidate grid of the pruned scan: building it costs ~cells*T distance evaluations per robot and solve, the
+  // rollouts K*T*(~100 instr): keep the grid below a few per cent of that
+  d.grid_max_cells = num_samples / 2 < 256 ? 256 : (num_samples / 2 > 16384 ? 16384 : num_samples / 2);
   if (d.planes > 65535) {
     delete h;
     return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");
@@ -328,6 +342,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
+  CU_NEW(cudaMalloc((void **)&d.grid_hdr, sizeof(GridHeader) * (size_t)d.R));
+  CU_NEW(cudaMemset(d.grid_hdr, 0, sizeof(GridHeader) * (size_t)d.R));
+  CU_NEW(cudaMalloc((void **)&d.grid_cells, sizeof(uint32_t) * (size_t)d.R * d.grid_max_cells));
   d.gathered = d.record;
 #undef CU_NEW
   h->path.resize(n_robots);
@@ -348,6 +365,7 @@ int mppi_destroy(mppi_handle h) {
   if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
   cudaFree(d.record); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
+  cudaFree(d.grid_hdr); cudaFree(d.grid_cells);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -622,19 +640,20 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
   if (n_iters < 1 || !ms) return fail(h, MPPI_ERR_INVALID, "n_iters >= 1 and ms != NULL required");
   if (!h->have_inputs) return fail(h, MPPI_ERR_STATE, "mppi_time_kernels before mppi_upload");
   CU_TRY(h, cudaSetDevice(h->device));
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[9];
   for (auto &e : ev) CU_TRY(h, cudaEventCreate(&e));
-  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const DeviceState &d = h->d;
   cudaStream_t s = h->stream;
-  const bool want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && d.nearest;
-  int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
-  if (want_nearest) scan = MPPI_SCAN_LITERAL;
+  bool want_nearest;
+  const int scan = effective_scan(h, &want_nearest);
   int rc = MPPI_OK;
   for (int it = 0; it <= n_iters && rc == MPPI_OK; ++it) {
     cudaEventRecord(ev[0], s);
     if (h->external_noise) launch_reset_cmin(d, s); else launch_noise(d, s);
     cudaEventRecord(ev[1], s);
+    if (scan == MPPI_SCAN_PRUNED) launch_candidate_grid(d, s);
+    cudaEventRecord(ev[7], s);
     launch_rollout_cost(d, scan, want_nearest, s);
     cudaEventRecord(ev[2], s);
     launch_weights(d, s);
@@ -653,15 +672,17 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     if (it == 0 || rc != MPPI_OK) continue;  // warm-up
     for (int k = 0; k < 6; ++k) {
       float t = 0.f;
-      cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+      cudaEventElapsedTime(&t, k == 1 ? ev[7] : ev[k], ev[k + 1]);
       acc[k] += t;
     }
     float t = 0.f;
     cudaEventElapsedTime(&t, ev[0], ev[6]);
     acc[6] += t;
+    cudaEventElapsedTime(&t, ev[1], ev[7]);
+    acc[7] += t;
   }
   for (auto &e : ev) cudaEventDestroy(e);
-  for (int k = 0; k < 7; ++k) ms[k] = (float)(acc[k] / n_iters);
+  for (int k = 0; k < 8; ++k) ms[k] = (float)(acc[k] / n_iters);
   return rc;
 }
 

@@ -19,6 +19,12 @@ struct SolveHeader {
   uint32_t pad[3];
 };
 
+// geometry of one robot's candidate grid (written by K0, read by K2): cell (ix, iy) = floor(fma(x, inv_h, cx)), ...
+struct GridHeader {
+  float x0, y0, h, inv_h, cx, cy;
+  int nx, ny;
+};
+
 // HBM layout owned by one handle.  R robots, K samples (this shard), T horizon, U controls, P = (T-1)*U planes.
 //   inbuf    one allocation, one H2D copy per solve:
 //     hdr      SolveHeader (padded to 256 B)
@@ -36,6 +42,8 @@ struct SolveHeader {
 //   outbuf   one allocation, one D2H copy per solve:  u_new [R][P], stats [R][4] = {c_min, sum w, ESS, -}
 //   nearest  [R][K][T]   int32, debug only
 //   counter  [1]         solve counter of the Philox stream, advanced on the device by the merge kernel
+//   grid_hdr [R], grid_cells [R][grid_max_cells]  candidate grid of the pruned scan (K0 -> K2): per cell the
+//                        range of window-point pairs that can hold the nearest point, lo | n << 16
 struct DeviceState {
   int model = 0, T = 0, U = 0;
   int K = 0, Kp = 0, R = 0, planes = 0, win_stride = 0, rec_stride = 0;
@@ -48,6 +56,10 @@ struct DeviceState {
   unsigned int *cmin = nullptr;
   uint32_t *counter = nullptr;
   int *nearest = nullptr;
+  GridHeader *grid_hdr = nullptr;
+  uint32_t *grid_cells = nullptr;
+  int grid_max_cells = 0;
+  float grid_h_min = 0.125f, grid_margin = 3.0f;
 };
 
 constexpr int kHeaderBytes = 256;
@@ -62,6 +74,8 @@ cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
 cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s);
+// K0  candidate grid of the pruned scan, once per robot and solve (mppi_rollout_pruned.cu)
+cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s);
 // K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
 cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s);
 bool pruned_scan_supported(int T, int planes);

@@ -3,38 +3,33 @@
 //
 // What it replaces: clamp (DD:98-99) + predict_States (DD:111-122) + calc_Cost / calc_MinDistance (DD:183-210)
 // [+ the ZMP loop FB:468-486 and cost FB:404-424], reference = /root/reference/src/{diff_drive,steering_diff_drive,
-// full_body}_mppi.cpp.  Per-sample arithmetic is the FP32 contract of mppi_math.h; the result is bit-identical to
-// rollout_cost_literal_kernel (and to the host twin) for every input -- the scan only SKIPS window points that
-// provably cannot be the minimum:
+// full_body}_mppi.cpp.  Per-sample arithmetic is the FP32 contract of mppi_math.h; the per-sample cost is
+// bit-identical to rollout_cost_literal_kernel (and to the host twin) for every input -- the scan only SKIPS
+// window points that provably cannot be the minimum.
 //
-//   * the T window points are grouped into leaves of 4 consecutive points (padded with copies of the last point);
-//     each leaf, each prefix [0,b) and each suffix [b,NB) of leaves has a bounding circle (centre c, radius rho),
-//     built once per CTA in shared memory;
-//   * per state, a thread scans a window of kWin consecutive leaves around the leaf that held its previous
-//     minimum (temporal coherence: a rollout moves <= v_max*dt per step), giving a candidate minimum `best`;
-//   * every point outside that window lies in one of kMid leaves either side or in the prefix / suffix beyond;
-//     a node is discarded when |p - c| > sqrt(best) + rho (triangle inequality), evaluated in the squared domain
-//     with a 2^-17 relative safety margin (>> the few-ulp rounding of the test itself), so a discarded point
-//     always has fl(d^2) > best;
-//   * if any node cannot be discarded the thread falls back to the full scan for that state.
-// min() is exact and order-independent, so the accumulated path cost has the same bits as the literal scan.
-// Cost per state is independent of T (about 12 exact distances + 6 circle tests instead of T distances).
-//
-// The distance evaluation uses Blackwell's packed FP32 pipe (sub/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2, two window
-// points per instruction, same IEEE roundings per element) and the 3-input FMNMX3.
+// How.  All K samples of a robot query the same T window points.  K0 (candidate_grid_kernel, once per robot and
+// solve) lays a uniform grid of square cells (side h) over the window's bounding box plus a margin and stores,
+// per cell, the smallest contiguous index range [lo, lo+n) that contains every window point that can be the
+// nearest one for ANY position inside the cell:
+//     with c the cell centre, r its half diagonal (inflated) and D_j = |c - r_j|:  for p in the cell
+//     | |p - r_j| - D_j | <= r, so a point with D_j > min_k D_k + 2r is strictly farther from p than the point
+//     that attains the minimum at c.  Candidates = { j : D_j <= D_min + 2r } (+ 1e-4 relative slack, four orders
+//     of magnitude above the FP32 rounding of the distances involved).
+// K2 looks the cell of each predicted state up (one FMA + float->int per axis, one 32-bit load) and evaluates
+// exact squared distances only for that range -- about 4-12 points instead of T, independent of T -- with
+// Blackwell's packed FP32 pipe (sub/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2, two window points per instruction,
+// the same IEEE roundings per element as mppi::dist2) and the 3-input FMNMX3.  States outside the grid scan the
+// whole window.  min() is exact and order independent, so the accumulated path cost has the literal scan's bits.
 #include "mppi_device.cuh"
 
 namespace mppi {
 
 namespace {
 
-constexpr int kLeaf = 4;   // window points per leaf
-constexpr int kWin = 3;    // leaves scanned around the tracked minimum
-constexpr int kMid = 2;    // leaves tested individually either side of the scanned window
-constexpr float kInflate = 1.0f + 1.0f / 262144.0f;  // 1 + 2^-18 on sqrt(best) and on every radius
-constexpr float kFar = 1.0e18f;                      // centre of an empty node: never within reach
-
 typedef unsigned long long u64;
+
+constexpr float kCellInflate = 1.002f;   // on the half diagonal: absorbs the rounding of the cell lookup
+constexpr float kCandSlack = 1.0001f;    // relative slack on the candidate threshold (squared domain)
 
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
   u64 r;
@@ -58,194 +53,231 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ float sqrt_approx(float a) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
 
-// minimum squared distance to the 4 points of one leaf; leaf = {x0,x1,y0,y1}, {x2,x3,y2,y3}
-__device__ __forceinline__ float leaf_min(const float4 *leaf, u64 xx, u64 yy) {
-  const float4 a = leaf[0], b = leaf[1];
-  float a0, a1, b0, b1;
-  unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
-  unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
-  return min3f(a0, a1, fminf(b0, b1));
-}
-
-// true when no point inside the node can be closer than sqrt(best): |p - c| > s + rho, squared domain.
-// node = {cx, cy, rho * kInflate, -}; s_up = sqrt(best) * kInflate (rounded-up estimate)
-__device__ __forceinline__ bool node_excluded(const float4 node, float x, float y, float s_up) {
-  const float dx = x - node.x, dy = y - node.y;
-  const float D2 = fmaf(dy, dy, dx * dx);
-  const float t = s_up + node.z;
-  return D2 > t * t;
-}
-
-struct ScanTables {
-  const float4 *pts;   // [2*NB]  leaf b = pts[2b], pts[2b+1]
-  const float4 *leaf;  // [NB + 2*kMid]  circle of leaf b at leaf[b + kMid]; empties either side
-  const float4 *pre;   // [NB + 1]  circle of leaves [0, b)
-  const float4 *suf;   // [NB + 1]  circle of leaves [b, NB)
-  int NB;
-};
-
-// Exact min_j min(d2(p, r_j), 1e4) over the whole window.  wl = first leaf of this thread's scan window (in/out).
-__device__ __forceinline__ float min_dist2_pruned(const ScanTables &tb, float x, float y, int &wl) {
+// min over the window pairs [q0, q0 + nq) of min(d2, best); pairs = {x0, x1, y0, y1}
+__device__ __forceinline__ float scan_pairs(const float4 *__restrict__ pairs, int q0, int nq, float x, float y,
+                                            float best) {
   const u64 xx = pack2(x, x), yy = pack2(y, y);
-  const float4 *w = tb.pts + 2 * wl;
-  float m[kWin];
-#pragma unroll
-  for (int k = 0; k < kWin; ++k) m[k] = leaf_min(w + 2 * k, xx, yy);
-  float best = kDist2Cap;
-#pragma unroll
-  for (int k = 0; k < kWin; ++k) best = fminf(best, m[k]);
-  const float s_up = sqrt_approx(best) * kInflate;
-  bool ok = node_excluded(tb.pre[max(wl - kMid, 0)], x, y, s_up);
-  ok = ok && node_excluded(tb.suf[min(wl + kWin + kMid, tb.NB)], x, y, s_up);
-#pragma unroll
-  for (int k = 0; k < kMid; ++k) {
-    ok = ok && node_excluded(tb.leaf[wl + k], x, y, s_up);                       // leaves wl-kMid .. wl-1
-    ok = ok && node_excluded(tb.leaf[wl + kMid + kWin + k], x, y, s_up);         // leaves wl+kWin .. wl+kWin+kMid-1
+  const float4 *p = pairs + q0;
+  for (int k = 0; k < nq; ++k) {
+    const float4 w = p[k];
+    float d0, d1;
+    unpack2(dist2_pair(xx, yy, pack2(w.x, w.y), pack2(w.z, w.w)), d0, d1);
+    best = min3f(best, d0, d1);
   }
-  if (ok) {
-    // keep the minimum in the middle of the window
-    if (m[0] == best && wl > 0) --wl;
-    else if (m[kWin - 1] == best && m[kWin / 2] != best && wl + kWin < tb.NB) ++wl;
-    return best;
-  }
-  // fallback: every leaf (still exact), re-centre on the leaf that holds the minimum
-  best = kDist2Cap;
-  int bl = wl + kWin / 2;
-  for (int b = 0; b < tb.NB; ++b) {
-    const float mb = leaf_min(tb.pts + 2 * b, xx, yy);
-    if (mb < best) {
-      best = mb;
-      bl = b;
-    }
-  }
-  wl = min(max(bl - kWin / 2, 0), tb.NB - kWin);
   return best;
 }
 
-// bounding circle of window points [j0, j1) (indices into the padded point list): bbox centre, max distance
-__device__ float4 bounding_circle(const float2 *pt, int j0, int j1) {
-  if (j1 <= j0) return make_float4(kFar, kFar, 0.f, 0.f);
-  float xmin = pt[j0].x, xmax = xmin, ymin = pt[j0].y, ymax = ymin;
-  for (int j = j0 + 1; j < j1; ++j) {
-    xmin = fminf(xmin, pt[j].x);
-    xmax = fmaxf(xmax, pt[j].x);
-    ymin = fminf(ymin, pt[j].y);
-    ymax = fmaxf(ymax, pt[j].y);
+struct GridView {
+  const uint32_t *cells;  // [ny][nx]: lo_pair | n_pairs << 16
+  float inv_h, cx, cy;    // cell index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy))
+  int nx, ny;
+  int all_pairs;          // (T + 1) / 2: the whole (padded) window
+};
+
+// Exact min_j min(d2(p, r_j), 1e4) over the whole window.
+__device__ __forceinline__ float min_dist2_grid(const GridView &g, const float4 *__restrict__ pairs, float x, float y) {
+  const int ix = __float2int_rd(fmaf(x, g.inv_h, g.cx));
+  const int iy = __float2int_rd(fmaf(y, g.inv_h, g.cy));
+  int q0 = 0, nq = g.all_pairs;
+  if ((unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny) {
+    const uint32_t e = __ldg(g.cells + iy * g.nx + ix);
+    q0 = (int)(e & 0xFFFFu);
+    nq = (int)(e >> 16);
   }
-  const float cx = 0.5f * (xmin + xmax), cy = 0.5f * (ymin + ymax);
-  float r2 = 0.f;
-  for (int j = j0; j < j1; ++j) r2 = fmaxf(r2, dist2(cx, cy, pt[j].x, pt[j].y));
-  // a NaN / inf window coordinate makes the node unusable: force the fallback scan
-  if (!(r2 < 1.0e30f)) return make_float4(0.f, 0.f, 1.0e18f, 0.f);
-  return make_float4(cx, cy, sqrtf(r2) * kInflate + 1.0e-30f, 0.f);
+  return scan_pairs(pairs, q0, nq, x, y, kDist2Cap);
 }
 
 }  // namespace
 
-size_t pruned_smem_bytes(int T, int planes) {
-  const int NB = (T + kLeaf - 1) / kLeaf;
-  // raw points (float2 x NB*4) | packed leaves (float4 x 2NB) | leaf circles | prefix | suffix | nominal
-  return sizeof(float2) * (size_t)NB * kLeaf + sizeof(float4) * ((size_t)2 * NB + (NB + 2 * kMid) + 2 * (NB + 1)) +
-         sizeof(float) * (size_t)planes;
+// ---------------------------------------------------------------------------------------------------------
+// K0: candidate grid (once per robot and solve)
+// ---------------------------------------------------------------------------------------------------------
+// grid = (cell blocks, robots), 128 threads, one thread per cell.  Every CTA re-derives the grid geometry from the
+// window (same arithmetic, same result); CTA 0 publishes it in ghdr[robot] for K2.
+__global__ void __launch_bounds__(128)
+    candidate_grid_kernel(const float *__restrict__ window, GridHeader *__restrict__ ghdr, uint32_t *__restrict__ cells,
+                          int T, int win_stride, int max_cells, float h_min, float margin) {
+  extern __shared__ __align__(16) float2 s_win[];
+  __shared__ float s_box[4];
+  __shared__ GridHeader s_h;
+  const int robot = blockIdx.y;
+  const float *g_win = window + (size_t)robot * win_stride;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) s_win[j] = make_float2(g_win[2 * j], g_win[2 * j + 1]);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    bool finite = true;
+    for (int j = threadIdx.x; j < T; j += 32) {
+      const float2 p = s_win[j];
+      finite = finite && (fabsf(p.x) < 1.0e15f) && (fabsf(p.y) < 1.0e15f);
+      xmin = fminf(xmin, p.x);
+      xmax = fmaxf(xmax, p.x);
+      ymin = fminf(ymin, p.y);
+      ymax = fmaxf(ymax, p.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+      xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+      ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    finite = __all_sync(0xffffffffu, finite);
+    if (threadIdx.x == 0) {
+      GridHeader gh;
+      gh.nx = gh.ny = 0;
+      gh.inv_h = gh.cx = gh.cy = 0.f;
+      gh.h = 0.f;
+      gh.x0 = gh.y0 = 0.f;
+      if (finite) {
+        const float w = (xmax - xmin) + 2.f * margin, hgt = (ymax - ymin) + 2.f * margin;
+        float h = fmaxf(h_min, sqrtf(w * hgt / (float)max_cells));
+        int nx = 0, ny = 0;
+        for (int it = 0; it < 64; ++it) {
+          nx = (int)ceilf(w / h);
+          ny = (int)ceilf(hgt / h);
+          if ((long long)nx * ny <= max_cells && nx < 32768 && ny < 32768) break;
+          h *= 1.05f;
+        }
+        if ((long long)nx * ny <= max_cells) {
+          gh.nx = nx;
+          gh.ny = ny;
+          gh.h = h;
+          gh.inv_h = 1.0f / h;
+          gh.x0 = xmin - margin;
+          gh.y0 = ymin - margin;
+          gh.cx = -gh.x0 * gh.inv_h;
+          gh.cy = -gh.y0 * gh.inv_h;
+        }
+      }
+      s_h = gh;
+      if (blockIdx.x == 0) ghdr[robot] = gh;
+    }
+  }
+  __syncthreads();
+  const GridHeader gh = s_h;
+  const int n_cells = gh.nx * gh.ny;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const int ix = cell % gh.nx, iy = cell / gh.nx;
+  const float ccx = gh.x0 + ((float)ix + 0.5f) * gh.h, ccy = gh.y0 + ((float)iy + 0.5f) * gh.h;
+  const float r = 0.70710678f * gh.h * kCellInflate + 1.0e-6f * (fabsf(ccx) + fabsf(ccy));
+  float m = INFINITY;
+  for (int j = 0; j < T; ++j) m = fminf(m, dist2(ccx, ccy, s_win[j].x, s_win[j].y));
+  const float reach = sqrtf(m) + 2.f * r;
+  const float thr = reach * reach * kCandSlack;
+  int lo = T, hi = -1;
+  for (int j = 0; j < T; ++j) {
+    if (dist2(ccx, ccy, s_win[j].x, s_win[j].y) <= thr) {
+      lo = min(lo, j);
+      hi = j;
+    }
+  }
+  // pairs of points; an empty candidate set can only arise from NaNs: scan everything
+  int q0 = 0, nq = (T + 1) / 2;
+  if (hi >= lo) {
+    q0 = lo >> 1;
+    nq = (hi >> 1) - q0 + 1;
+  }
+  cells[(size_t)robot * max_cells + cell] = (uint32_t)q0 | ((uint32_t)nq << 16);
+}
+
+cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
+  dim3 grid((d.grid_max_cells + 127) / 128, d.R);
+  const size_t smem = sizeof(float2) * (size_t)d.T;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(candidate_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  candidate_grid_kernel<<<grid, 128, smem, s>>>(d.window, d.grid_hdr, d.grid_cells, d.T, d.win_stride, d.grid_max_cells,
+                                                d.grid_h_min, d.grid_margin);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 (pruned)
+// ---------------------------------------------------------------------------------------------------------
+size_t pruned_smem_bytes(int T, int planes, int U) {
+  // window pairs {x0,x1,y0,y1} x ceil(T/2) | nominal padded by two control steps
+  return sizeof(float4) * (size_t)((T + 1) / 2) + sizeof(float) * ((size_t)planes + 2 * U);
 }
 
 template <int MODEL>
 __global__ void __launch_bounds__(128)
     rollout_cost_pruned_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ eps,
                                const float *__restrict__ nominal, const float *__restrict__ window,
-                               const float *__restrict__ state, float *__restrict__ cost,
-                               unsigned int *__restrict__ cmin, int K, int Kp, int planes, int win_stride, int T) {
+                               const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
+                               const uint32_t *__restrict__ cells, float *__restrict__ cost,
+                               unsigned int *__restrict__ cmin, int K, int Kp, int planes, int win_stride, int T,
+                               int max_cells) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ SolveParams sP;
   __shared__ float s_red[32];
   const int robot = blockIdx.y;
-  const int NB = (T + kLeaf - 1) / kLeaf;
-  float4 *s_pts = reinterpret_cast<float4 *>(smem_raw);
-  float4 *s_leaf = s_pts + 2 * NB;
-  float4 *s_pre = s_leaf + NB + 2 * kMid;
-  float4 *s_suf = s_pre + NB + 1;
-  float2 *s_raw = reinterpret_cast<float2 *>(s_suf + NB + 1);
-  float *s_nom = reinterpret_cast<float *>(s_raw + NB * kLeaf);
+  const int NP = (T + 1) / 2;
+  float4 *s_pairs = reinterpret_cast<float4 *>(smem_raw);
+  float *s_nom = reinterpret_cast<float *>(s_pairs + NP);
 
-  // ---- prologue: stage the window, build the bounding circles -------------------------------------------
   const float *g_win = window + (size_t)robot * win_stride;
   load_params_to_shared(&sP, hdr);
-  for (int j = threadIdx.x; j < NB * kLeaf; j += blockDim.x) {
-    const int js = min(j, T - 1);  // pad with copies of the last point (does not change any minimum)
-    s_raw[j] = make_float2(g_win[2 * js], g_win[2 * js + 1]);
+  for (int q = threadIdx.x; q < NP; q += blockDim.x) {
+    const int j0 = 2 * q, j1 = min(2 * q + 1, T - 1);  // odd T: the last point twice (no effect on a minimum)
+    s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
   }
-  for (int j = threadIdx.x; j < planes; j += blockDim.x) s_nom[j] = nominal[(size_t)robot * planes + j];
-  __syncthreads();
-  for (int b = threadIdx.x; b < 2 * NB; b += blockDim.x) {
-    const float2 p0 = s_raw[2 * b], p1 = s_raw[2 * b + 1];
-    s_pts[b] = make_float4(p0.x, p1.x, p0.y, p1.y);
-  }
-  for (int k = threadIdx.x; k < NB + 2 * kMid; k += blockDim.x) {
-    const int b = k - kMid;
-    s_leaf[k] = (b >= 0 && b < NB) ? bounding_circle(s_raw, b * kLeaf, (b + 1) * kLeaf) : make_float4(kFar, kFar, 0.f, 0.f);
-  }
-  // prefix / suffix circles: thread pairs from the top so the long ones do not all land in warp 0
-  for (int k = blockDim.x - 1 - threadIdx.x; k < 2 * (NB + 1); k += blockDim.x) {
-    const int b = k >> 1;
-    if (k & 1) s_suf[b] = bounding_circle(s_raw, b * kLeaf, NB * kLeaf);
-    else s_pre[b] = bounding_circle(s_raw, 0, b * kLeaf);
-  }
+  for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
+    s_nom[j] = j < planes ? nominal[(size_t)robot * planes + j] : 0.f;
   __syncthreads();
 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float c = 0.f;
   if (i < K) {
-    const ScanTables tb{s_pts, s_leaf, s_pre, s_suf, NB};
+    const GridHeader gh = ghdr[robot];
+    const GridView gv{cells + (size_t)robot * max_cells, gh.inv_h, gh.cx, gh.cy, gh.nx, gh.ny, NP};
     const float *st = state + (size_t)robot * 8;
-    const float *e = eps + (size_t)robot * planes * Kp + i;
     const int steps = T - 1;
-    const int Tc = num_cost_states(MODEL, T);
+    // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
+    // looks at the last two states, FB:409)
+    const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
     float x = st[0], y = st[1], yaw = st[2];
     float roll = MODEL == kFullBody ? st[3] : 0.f;
     float pitch = MODEL == kFullBody ? st[4] : 0.f;
     const float sigma = sP.sigma, dt = sP.dt, v_ref = sP.v_ref;
     const bool steer_off = MODEL == kFullBody && sP.steer_off;
+    float lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      lo[u] = sP.u_min[u];
+      hi[u] = sP.u_max[u];
+    }
     CostAcc acc;
     float cur[U], nxt[U], raw[U];
+    // normals of control step t live at e_t = eps + (t*U + u)*Kp; the pointer stops at the last step
+    const size_t step_stride = (size_t)U * Kp;
+    const float *e_ptr = eps + (size_t)robot * planes * Kp + i;
+    int t_loaded = 0;
+    auto load_raw = [&]() {  // normals of step min(t_loaded, steps-1); past the end the values are never used
 #pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = nxt[u] = raw[u] = 0.f;
-    auto load_raw = [&](int t) {
-      if (t < steps) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) raw[u] = __ldcs(e + (size_t)(t * U + u) * Kp);
-      }
+      for (int u = 0; u < U; ++u) raw[u] = __ldcs(e_ptr + (size_t)u * Kp);
+      if (t_loaded + 1 < steps) e_ptr += step_stride;
+      ++t_loaded;
     };
-    auto make = [&](int t, float *dst) {  // sampling (D5) from the prefetched normals of step t
-      if (t < steps) {
+    auto make = [&](int t, float *dst) {  // sampling (D5); s_nom is padded so t may run two steps past the end
 #pragma unroll
-        for (int u = 0; u < U; ++u) dst[u] = sample_control(raw[u], sigma, s_nom[t * U + u], sP.u_min[u], sP.u_max[u]);
-        if (steer_off) dst[2] = 0.f;  // FB:517
-      }
+      for (int u = 0; u < U; ++u) dst[u] = sample_control(raw[u], sigma, s_nom[t * U + u], lo[u], hi[u]);
+      if (steer_off) dst[2] = 0.f;  // FB:517
     };
-    load_raw(0);
+    load_raw();
     make(0, cur);
-    load_raw(1);
+    load_raw();
     make(1, nxt);
-    load_raw(2);
-    int wl = 0;
-    for (int t = 0; t < T; ++t) {
-      const bool has_step = t < steps;
-      if (t < Tc) acc.path += min_dist2_pruned(tb, x, y, wl);
-      if (MODEL != kFullBody) {
-        if (has_step) {
-          const float dv = cur[0] - v_ref;
-          acc.vel = fmaf(dv, dv, acc.vel);
-        }
-      } else if (t < Tc) {
-        const float dv = cur[0] - v_ref;
-        acc.vel = fmaf(dv, dv, acc.vel);
+    load_raw();
+    for (int t = 0; t < n_iter; ++t) {
+      acc.path += min_dist2_grid(gv, s_pairs, x, y);
+      const float dv = cur[0] - v_ref;
+      acc.vel = fmaf(dv, dv, acc.vel);
+      if (MODEL == kFullBody) {
         float zx, zy;
         zmp_model(sP, cur[0], nxt[0], cur[1], cur[2], cur[3], nxt[3], cur[4], nxt[4], roll, pitch, zx, zy);
         acc.zmp = fmaf(zy, zy, acc.zmp);
@@ -253,19 +285,18 @@ __global__ void __launch_bounds__(128)
         acc.droll = fmaf(dr, dr, acc.droll);
         if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
       }
-      if (has_step) {
-        const float heading = MODEL == kDiffDrive ? yaw : yaw + cur[2];
-        step_pose(x, y, yaw, cur[0], cur[1], heading, dt);
-        if (MODEL == kFullBody) {
-          roll = fmaf(cur[3], dt, roll);
-          pitch = fmaf(cur[4], dt, pitch);
-        }
+      const float heading = MODEL == kDiffDrive ? yaw : yaw + cur[2];
+      step_pose(x, y, yaw, cur[0], cur[1], heading, dt);
+      if (MODEL == kFullBody) {
+        roll = fmaf(cur[3], dt, roll);
+        pitch = fmaf(cur[4], dt, pitch);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) cur[u] = nxt[u];
       make(t + 2, nxt);
-      load_raw(t + 3);
+      load_raw();
     }
+    if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, s_pairs, x, y);  // state T-1: path term only (D1)
     c = combine_cost(sP, acc, MODEL == kFullBody ? st[2] - st[5] : 0.f);
     cost[(size_t)robot * K + i] = c;
   }
@@ -274,7 +305,7 @@ __global__ void __launch_bounds__(128)
 
 cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
   dim3 grid((d.K + 127) / 128, d.R);
-  const size_t smem = pruned_smem_bytes(d.T, d.planes);
+  const size_t smem = pruned_smem_bytes(d.T, d.planes, d.U);
 #define MPPI_LAUNCH_PRUNED(M)                                                                                    \
   do {                                                                                                           \
     if (smem > 48 * 1024) {                                                                                      \
@@ -282,8 +313,9 @@ cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
     }                                                                                                            \
-    rollout_cost_pruned_kernel<M><<<grid, 128, smem, s>>>(d.hdr, d.eps, d.nominal, d.window, d.state, d.cost,    \
-                                                          d.cmin, d.K, d.Kp, d.planes, d.win_stride, d.T);       \
+    rollout_cost_pruned_kernel<M><<<grid, 128, smem, s>>>(d.hdr, d.eps, d.nominal, d.window, d.state,            \
+                                                          d.grid_hdr, d.grid_cells, d.cost, d.cmin, d.K, d.Kp,   \
+                                                          d.planes, d.win_stride, d.T, d.grid_max_cells);        \
   } while (0)
   switch (d.model) {
     case kDiffDrive: MPPI_LAUNCH_PRUNED(kDiffDrive); break;
@@ -294,9 +326,9 @@ cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// worth it (and the tables fit) only for windows of more than a few leaves
+// worth it only for windows of more than a couple of dozen points; the 16-bit pair fields bound T
 bool pruned_scan_supported(int T, int planes) {
-  return (T + kLeaf - 1) / kLeaf >= kWin + 2 * kMid && pruned_smem_bytes(T, planes) <= 200 * 1024;
+  return T >= 24 && T <= 65534 && pruned_smem_bytes(T, planes, kMaxControls) <= 200 * 1024;
 }
 
 }  // namespace mppi

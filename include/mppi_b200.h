@@ -68,7 +68,9 @@ typedef enum {
 } mppi_debug_flags;
 
 /* Implementation of the nearest-window-point scan inside the fused rollout+cost kernel. Both are exact and
- * bit-identical in every output; LITERAL evaluates all T window points per state (DD:186-190). */
+ * bit-identical in every output; LITERAL evaluates all T window points per state (DD:186-190), PRUNED only the
+ * points that a per-solve candidate grid cannot rule out.  AUTO = PRUNED when T >= 24, LITERAL below; LITERAL is
+ * forced while MPPI_DEBUG_NEAREST is on (it is the kernel that records the argmin). */
 typedef enum {
   MPPI_SCAN_AUTO = 0,
   MPPI_SCAN_LITERAL = 1,
@@ -149,9 +151,10 @@ int mppi_get_stats(mppi_handle h, int robot, double *stats);
 int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int *num_controls, int *n_robots);
 /* Per-kernel device time of the solve (CUDA events between the launches on the handle's stream), averaged over
  * n_iters solves after one warm-up: ms[0..5] = noise, rollout+cost, weights, weighted controls, finalize, merge
- * (collective time, when sharded, is included in ms[5]); ms[6] = whole enqueue.  Advances the warm start and the
- * solve counter like n_iters + 1 calls of mppi_enqueue. */
-int mppi_time_kernels(mppi_handle h, int n_iters, float *ms /* [7] */);
+ * (collective time, when sharded, is included in ms[5]); ms[6] = whole enqueue; ms[7] = candidate grid of the
+ * pruned scan (0 when the literal scan runs).  Advances the warm start and the solve counter like n_iters + 1
+ * calls of mppi_enqueue. */
+int mppi_time_kernels(mppi_handle h, int n_iters, float *ms /* [8] */);
 /* number of kernel launches issued by the last mppi_enqueue (bench.py's gpu_launches claim) */
 int mppi_last_launch_count(mppi_handle h);
 
