@@ -277,6 +277,8 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   h->params = *params;
   h->k_global = num_samples;
   DeviceState &d = h->d;
+  d.key0 = (uint32_t)h->seed;
+  d.key1 = (uint32_t)(h->seed >> 32);
   d.model = model;
   d.T = horizon;
   d.U = h->U;
@@ -423,7 +425,10 @@ int mppi_set_window(mppi_handle h, int robot, const double *window_xyyaw) {
 int mppi_set_seed(mppi_handle h, uint64_t seed, uint64_t first_solve_counter) {
   if (!h) return MPPI_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
+  if (seed != h->seed) invalidate_graphs(h);  // the key is a kernel argument of the captured noise node
   h->seed = seed;
+  h->d.key0 = (uint32_t)seed;
+  h->d.key1 = (uint32_t)(seed >> 32);
   uint32_t c = (uint32_t)first_solve_counter;
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   CU_TRY(h, cudaMemcpy(h->d.counter, &c, sizeof c, cudaMemcpyHostToDevice));

@@ -13,7 +13,7 @@ namespace mppi {
 struct SolveHeader {
   SolveParams P;
   float inv_lambda;
-  uint32_t key0, key1;    // Philox key = 64-bit seed
+  uint32_t key0, key1;    // Philox key = 64-bit seed (informational; K1 takes the key as a kernel argument)
   uint32_t robot_offset;  // global index of robot 0 of this handle
   uint32_t q_offset;      // global sample offset of this shard / 4
   uint32_t pad[3];
@@ -48,6 +48,7 @@ struct DeviceState {
   int model = 0, T = 0, U = 0;
   int K = 0, Kp = 0, R = 0, planes = 0, win_stride = 0, rec_stride = 0;
   int nb3 = 0, nchunk = 0, n_ranks = 1;
+  uint32_t key0 = 0, key1 = 0;  // Philox key = 64-bit seed (kernel argument of K1)
   SolveHeader *hdr = nullptr;
   float *window = nullptr, *state = nullptr, *nominal = nullptr;
   float *eps = nullptr, *cost = nullptr, *weight = nullptr, *wpart = nullptr, *npart = nullptr;

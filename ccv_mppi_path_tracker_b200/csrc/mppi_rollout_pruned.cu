@@ -54,39 +54,58 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
   return r;
 }
 
-// min over the window pairs [q0, q0 + nq) of min(d2, best); pairs = {x0, x1, y0, y1}
-__device__ __forceinline__ float scan_pairs(const float4 *__restrict__ pairs, int q0, int nq, float x, float y,
+// min over the window pairs [q0, q0 + 2*n2) of min(d2, best); pairs = {x0, x1, y0, y1}.  Two pairs (four window
+// points) per iteration; scanning a few points more than the candidate range is always safe (they are window
+// points too), so the range is rounded up instead of predicated.
+__device__ __forceinline__ float scan_pairs(const float4 *__restrict__ pairs, int q0, int n2, float x, float y,
                                             float best) {
   const u64 xx = pack2(x, x), yy = pack2(y, y);
   const float4 *p = pairs + q0;
-  for (int k = 0; k < nq; ++k) {
-    const float4 w = p[k];
-    float d0, d1;
-    unpack2(dist2_pair(xx, yy, pack2(w.x, w.y), pack2(w.z, w.w)), d0, d1);
-    best = min3f(best, d0, d1);
+#pragma unroll 1
+  for (int k = 0; k < n2; ++k, p += 2) {
+    const float4 a = p[0], b = p[1];
+    float a0, a1, b0, b1;
+    unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
+    unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
+    best = min3f(best, a0, a1);
+    best = min3f(best, b0, b1);
   }
   return best;
 }
 
 struct GridView {
-  const uint32_t *cells;  // [ny][nx]: lo_pair | n_pairs << 16
+  const uint32_t *cells;  // [ny][nx]: first pair | (number of 2-pair iterations) << 16
   float inv_h, cx, cy;    // cell index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy))
   int nx, ny;
-  int all_pairs;          // (T + 1) / 2: the whole (padded) window
+  int all_n2;             // iterations that cover the whole (padded) window
 };
 
 // Exact min_j min(d2(p, r_j), 1e4) over the whole window.
 __device__ __forceinline__ float min_dist2_grid(const GridView &g, const float4 *__restrict__ pairs, float x, float y) {
   const int ix = __float2int_rd(fmaf(x, g.inv_h, g.cx));
   const int iy = __float2int_rd(fmaf(y, g.inv_h, g.cy));
-  int q0 = 0, nq = g.all_pairs;
+  int q0 = 0, n2 = g.all_n2;
   if ((unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny) {
-    const uint32_t e = __ldg(g.cells + iy * g.nx + ix);
+    const uint32_t e = __ldg(g.cells + (unsigned)(iy * g.nx + ix));
     q0 = (int)(e & 0xFFFFu);
-    nq = (int)(e >> 16);
+    n2 = (int)(e >> 16);
   }
-  return scan_pairs(pairs, q0, nq, x, y, kDist2Cap);
+  return scan_pairs(pairs, q0, n2, x, y, kDist2Cap);
 }
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, so the normals of future control
+// steps stream in behind the arithmetic without ever blocking a register scoreboard
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kRing = 4;  // ring of control steps in flight per thread (prefetch distance: two iterations)
 
 }  // namespace
 
@@ -174,13 +193,13 @@ __global__ void __launch_bounds__(128)
       hi = j;
     }
   }
-  // pairs of points; an empty candidate set can only arise from NaNs: scan everything
-  int q0 = 0, nq = (T + 1) / 2;
+  // pairs of points, two pairs per scan iteration; an empty candidate set can only arise from NaNs: scan everything
+  int q0 = 0, n2 = ((T + 1) / 2 + 1) / 2;
   if (hi >= lo) {
     q0 = lo >> 1;
-    nq = (hi >> 1) - q0 + 1;
+    n2 = ((hi >> 1) - q0 + 2) >> 1;
   }
-  cells[(size_t)robot * max_cells + cell] = (uint32_t)q0 | ((uint32_t)nq << 16);
+  cells[(size_t)robot * max_cells + cell] = (uint32_t)q0 | ((uint32_t)n2 << 16);
 }
 
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
@@ -199,8 +218,8 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
 // K2 (pruned)
 // ---------------------------------------------------------------------------------------------------------
 size_t pruned_smem_bytes(int T, int planes, int U) {
-  // window pairs {x0,x1,y0,y1} x ceil(T/2) | nominal padded by two control steps
-  return sizeof(float4) * (size_t)((T + 1) / 2) + sizeof(float) * ((size_t)planes + 2 * U);
+  // window pairs {x0,x1,y0,y1} x (ceil(T/2) + 1 pad) | ring of normals [kRing][U][128] | nominal padded by two steps
+  return sizeof(float4) * (size_t)((T + 1) / 2 + 1) + sizeof(float) * ((size_t)kRing * U * 128 + (size_t)planes + 2 * U);
 }
 
 template <int MODEL>
@@ -215,15 +234,19 @@ __global__ void __launch_bounds__(128)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ SolveParams sP;
   __shared__ float s_red[32];
+  __shared__ GridHeader s_gh;
   const int robot = blockIdx.y;
   const int NP = (T + 1) / 2;
   float4 *s_pairs = reinterpret_cast<float4 *>(smem_raw);
-  float *s_nom = reinterpret_cast<float *>(s_pairs + NP);
+  float *s_eps = reinterpret_cast<float *>(s_pairs + NP + 1);
+  float *s_nom = s_eps + kRing * U * 128;
 
   const float *g_win = window + (size_t)robot * win_stride;
   load_params_to_shared(&sP, hdr);
-  for (int q = threadIdx.x; q < NP; q += blockDim.x) {
-    const int j0 = 2 * q, j1 = min(2 * q + 1, T - 1);  // odd T: the last point twice (no effect on a minimum)
+  if (threadIdx.x == 0) s_gh = ghdr[robot];
+  for (int q = threadIdx.x; q < NP + 1; q += blockDim.x) {
+    // odd T and the pad pair: the last point again (no effect on a minimum)
+    const int j0 = min(2 * q, T - 1), j1 = min(2 * q + 1, T - 1);
     s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
   }
   for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
@@ -233,8 +256,7 @@ __global__ void __launch_bounds__(128)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float c = 0.f;
   if (i < K) {
-    const GridHeader gh = ghdr[robot];
-    const GridView gv{cells + (size_t)robot * max_cells, gh.inv_h, gh.cx, gh.cy, gh.nx, gh.ny, NP};
+    const GridView gv{cells + (size_t)robot * max_cells, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx, s_gh.ny, (NP + 1) / 2};
     const float *st = state + (size_t)robot * 8;
     const int steps = T - 1;
     // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
@@ -252,27 +274,33 @@ __global__ void __launch_bounds__(128)
       hi[u] = sP.u_max[u];
     }
     CostAcc acc;
-    float cur[U], nxt[U], raw[U];
-    // normals of control step t live at e_t = eps + (t*U + u)*Kp; the pointer stops at the last step
+    float cur[U], nxt[U];
+    // normals of control step t: eps[(t*U + u)*Kp + i], streamed through this thread's column of the ring
     const size_t step_stride = (size_t)U * Kp;
     const float *e_ptr = eps + (size_t)robot * planes * Kp + i;
-    int t_loaded = 0;
-    auto load_raw = [&]() {  // normals of step min(t_loaded, steps-1); past the end the values are never used
+    float *ring = s_eps + threadIdx.x;
+    int t_issue = 0;
+    auto issue = [&]() {  // start the copy of step t_issue (nothing past the last step), one commit group per step
+      if (t_issue < steps) {
+        float *dst = ring + (t_issue % kRing) * (U * 128);
 #pragma unroll
-      for (int u = 0; u < U; ++u) raw[u] = __ldcs(e_ptr + (size_t)u * Kp);
-      if (t_loaded + 1 < steps) e_ptr += step_stride;
-      ++t_loaded;
+        for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 128, e_ptr + (size_t)u * Kp);
+        e_ptr += step_stride;
+      }
+      cp_async_commit();
+      ++t_issue;
     };
-    auto make = [&](int t, float *dst) {  // sampling (D5); s_nom is padded so t may run two steps past the end
+    auto make = [&](int t, float *dst) {  // sampling (D5); past the last step the result is never used
+      const float *src = ring + (t % kRing) * (U * 128);
 #pragma unroll
-      for (int u = 0; u < U; ++u) dst[u] = sample_control(raw[u], sigma, s_nom[t * U + u], lo[u], hi[u]);
+      for (int u = 0; u < U; ++u) dst[u] = sample_control(src[u * 128], sigma, s_nom[t * U + u], lo[u], hi[u]);
       if (steer_off) dst[2] = 0.f;  // FB:517
     };
-    load_raw();
+#pragma unroll
+    for (int k = 0; k < kRing; ++k) issue();
+    cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
     make(0, cur);
-    load_raw();
     make(1, nxt);
-    load_raw();
     for (int t = 0; t < n_iter; ++t) {
       acc.path += min_dist2_grid(gv, s_pairs, x, y);
       const float dv = cur[0] - v_ref;
@@ -293,8 +321,10 @@ __global__ void __launch_bounds__(128)
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+      // step t+2 was issued two iterations ago (slot (t+2) % kRing); the slot of step t+4 held step t, consumed
+      issue();
+      cp_async_wait<2>();
       make(t + 2, nxt);
-      load_raw();
     }
     if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, s_pairs, x, y);  // state T-1: path term only (D1)
     c = combine_cost(sP, acc, MODEL == kFullBody ? st[2] - st[5] : 0.f);

@@ -120,11 +120,11 @@ def test_philox_noise_tensor():
     for (t, i, u) in [(0, 0, 0), (3, 17, 2), (28, 4095, 1), (11, 2049, 0)]:
         r = philox4x32_10([i // 4, t * 3 + u, 0, 7], [1234, 0])
         pair = 0 if (i % 4) < 2 else 2
-        u1 = ((r[pair] >> 8) + 0.5) * 2.0 ** -24
-        ang = np.int32(np.uint32(r[pair + 1])) * (np.pi * 2.0 ** -31)
+        u1 = 1.0 - (r[pair] >> 9) * 2.0 ** -23
+        ang = 2 * np.pi * (r[pair + 1] >> 9) * 2.0 ** -23
         rad = np.sqrt(-2.0 * np.log(u1))
         z = rad * (np.cos(ang) if (i % 2) == 0 else np.sin(ang))
-        assert abs(e1[t, i, u] - z) < 2e-5 * max(1.0, abs(z)), (t, i, u, e1[t, i, u], z)
+        assert abs(e1[t, i, u] - z) < 1e-5 * max(1.0, abs(z)) + 2e-6, (t, i, u, e1[t, i, u], z)
 
 
 def test_batched_robots_equal_single_robot_solves():
