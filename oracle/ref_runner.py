@@ -1,0 +1,60 @@
+"""Run one MPPI cycle of the UNMODIFIED reference node (oracle/_ref/ref_{dd,sd,fb}, built by oracle/ref_shim).
+TEST INFRASTRUCTURE ONLY: used by tests/test_oracle_vs_ref.py and tests/golden/make_golden.py in the build
+container, where /root/reference is mounted.  The GPU box only sees the golden vectors made from it."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = {"diff_drive": "ref_dd", "steering": "ref_sd", "full_body": "ref_fb"}
+NUM_CONTROLS = {"diff_drive": 2, "steering": 3, "full_body": 5}
+NUM_STATES = {"diff_drive": 3, "steering": 3, "full_body": 5}
+
+
+def available():
+    return all(os.path.exists(os.path.join(_HERE, "_ref", b)) for b in BIN.values())
+
+
+def run(model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
+    """node_params: the node's ROS parameters by their reference names (ccv_mppi_path_tracker_b200.params.node_params
+    with `lambda_` -> `lambda`); horizon / num_samples are overridden by T / K."""
+    U, S = NUM_CONTROLS[model], NUM_STATES[model]
+    p = {("lambda" if k == "lambda_" else k): float(v) for k, v in node_params.items()}
+    p["horizon"] = float(T)
+    p["num_samples"] = float(K)
+    path_xy = np.ascontiguousarray(path_xy, dtype=np.float64).reshape(-1, 2)
+    st = np.zeros(5)
+    st[:S] = np.asarray(state, dtype=np.float64).reshape(S)
+    eps = np.ascontiguousarray(eps, dtype=np.float32).reshape(T - 1, K, U)
+    u0 = np.ascontiguousarray(u_nominal, dtype=np.float64).reshape(T - 1, U)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<4i", K, T, path_xy.shape[0], len(p)))
+            for k, v in p.items():
+                f.write(k.encode()[:31].ljust(32, b"\0"))
+                f.write(struct.pack("<d", v))
+            f.write(st.tobytes())
+            f.write(struct.pack("<d", float(dt)))
+            f.write(path_xy.tobytes())
+            f.write(u0.tobytes())
+            f.write(eps.tobytes())
+        subprocess.run([os.path.join(_HERE, "_ref", BIN[model]), fin, fout], check=True, stderr=subprocess.DEVNULL)
+        raw = open(fout, "rb").read()
+    off = 0
+
+    def take(n, dtype=np.float64):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=n, offset=off)
+        off += a.nbytes
+        return a.copy()
+
+    out = {"yaw_used": float(take(1)[0]), "window": take(3 * T).reshape(T, 3), "cost": take(K), "weights": take(K),
+           "u_new": take((T - 1) * U).reshape(T - 1, U), "states": take(K * T * S).reshape(K, T, S)}
+    if model == "full_body":
+        out["zmp"] = take(K * max(T - 2, 0) * 2).reshape(K, max(T - 2, 0), 2)
+    out["current_index"] = int(take(1, np.int32)[0])
+    return out

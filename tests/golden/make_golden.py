@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Generate the golden vectors of tests/golden/*.npz from the UNMODIFIED reference nodes (oracle/_ref, built by
+`make ref` from /root/reference -- available in the build container only).  Each file holds the inputs of one MPPI
+cycle (parameters, state, path, warm start, the standard-normal noise tensor) and what the reference's own
+predict_States / calc_Weights / calc_Cost / determine_OptimalSolution produced for them.
+
+    python tests/golden/make_golden.py
+
+Reference UB handled as documented in oracle/ref_shim/ref_driver.cpp: the out-of-bounds v_[T-1] read is 0.0.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from common import make_case  # noqa: E402
+from oracle import ref_runner  # noqa: E402
+from ccv_mppi_path_tracker_b200 import paths  # noqa: E402
+
+CASES = [
+    # name, model, K, T, seed, extra overrides, path kind
+    ("dd_launch_K96_T15", "diff_drive", 96, 15, 101, {}, "launch"),
+    ("dd_tailclamp_K64_T40", "diff_drive", 64, 40, 102, {}, "launch_near_end"),
+    ("dd_datacsv_K64_T15", "diff_drive", 64, 15, 103, {}, "one_point"),
+    ("sd_launch_K96_T15", "steering", 96, 15, 104, {}, "launch"),
+    ("sd_K48_T50", "steering", 48, 50, 105, {}, "launch"),
+    ("fb_allterms_K96_T15", "full_body", 96, 15, 106, {"roll_off": False}, "launch"),
+    ("fb_rolloff_K64_T15", "full_body", 64, 15, 107, {"roll_off": True}, "launch"),
+    ("fb_steeroff_K64_T20", "full_body", 64, 20, 108, {"roll_off": False, "steer_off": True}, "launch"),
+    ("dd_defaults_K64_T15", "diff_drive", 64, 15, 109, {"launch": False}, "launch"),
+]
+
+
+def main():
+    if not ref_runner.available():
+        raise SystemExit("oracle/_ref is missing: run `make ref` where /root/reference is mounted")
+    for name, model, K, T, seed, ov, kind in CASES:
+        ov = dict(ov)
+        launch = ov.pop("launch", True)
+        case = make_case(model, K, T, seed=seed, launch=launch, **ov)
+        path, state = case["path"], case["state"].copy()
+        if kind == "one_point":
+            path = np.array([[-5.45606, -6.61448]])  # /root/reference/data/data.csv:1
+            state[:2] = [-5.2, -6.4]
+        elif kind == "launch_near_end":
+            state[:2] = path[-12] + [0.05, -0.08]
+        rng = np.random.default_rng(seed)
+        u0 = case["u0"] + 0.1 * rng.standard_normal(case["u0"].shape)
+        r = ref_runner.run(model, case["p"], K, T, state, case["dt"], path, case["eps"], u0)
+        keys = sorted(case["p"])
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"), model=model, K=K, T=T, dt=case["dt"], state=state, path=path,
+            eps=case["eps"], u0=u0, param_names=np.array(keys), param_values=np.array([float(case["p"][k]) for k in keys]),
+            **{"ref_" + k: v for k, v in r.items()})
+        print(name, "cost range", r["cost"].min(), r["cost"].max(), "u_new[0]", r["u_new"][0])
+
+
+if __name__ == "__main__":
+    main()

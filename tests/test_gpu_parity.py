@@ -358,3 +358,34 @@ def test_production_path_matches_oracle(model, K, T):
     assert np.array_equal(cost.view(np.uint32), tw["cost"].view(np.uint32))
     o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], eps, case["u0"])
     assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+
+
+# ---- against the UNMODIFIED reference nodes' own outputs (committed golden cycles) -----------------------------
+
+from common import golden_names, load_golden, oob_cost_offset  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_golden_reference_cycle(name):
+    g = load_golden(name)
+    model, K, T = g["model"], g["K"], g["T"]
+    ov = {k: v for k, v in g["p"].items() if k not in ("horizon", "num_samples")}
+    ctl = CONTROLLERS[model](launch=False, horizon=T, num_samples=K, **ov)
+    try:
+        ctl.set_path(g["path"])
+        ctl.set_noise(g["eps"][None])
+        ctl.optimal_solution[0] = g["u0"]
+        u_gpu = ctl.solve(g["state"], g["dt"]).copy()
+        cost = ctl.costs()
+        window, cur = ctl.window()
+    finally:
+        ctl.close()
+    ref = g["ref"]
+    assert cur == int(ref["current_index"]) and np.array_equal(window, ref["window"])
+    c_ref = ref["cost"] - oob_cost_offset(g)
+    assert np.all(np.abs(cost - c_ref) <= COST_RTOL * np.abs(c_ref) + COST_ATOL)
+    rng_ = np.array(g["sp"]["u_max"][: g["U"]]) - np.array(g["sp"]["u_min"][: g["U"]])
+    err = np.abs(u_gpu - ref["u_new"]) / np.where(rng_ > 0, rng_, 1.0)
+    # cost ~1e3 (tail-clamped windows): one FP32 ulp of the cost is 6e-5 -> weight error 6e-5 / lambda
+    tol = U_TOL if c_ref.max() < 300 else 5e-3
+    assert err.max() <= tol, (name, err.max())
