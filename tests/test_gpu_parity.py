@@ -389,3 +389,31 @@ def test_gpu_matches_golden_reference_cycle(name):
     # cost ~1e3 (tail-clamped windows): one FP32 ulp of the cost is 6e-5 -> weight error 6e-5 / lambda
     tol = U_TOL if c_ref.max() < 300 else 5e-3
     assert err.max() <= tol, (name, err.max())
+
+
+# ---- the C++ host classes (csrc/host/controllers.hpp) through the ROS-free harness ----------------------------
+
+def _run_harness(*args):
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ccv_mppi_path_tracker_b200", "mppi_harness")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    out = subprocess.run([exe, *args], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    return json.loads(out[-1]), out[:-1]
+
+
+@pytest.mark.parametrize("model,extra", [("dd", []), ("sd", []), ("fb", ["--param", "roll_off=0"])])
+def test_cpp_harness_tracks_the_launch_path(model, extra):
+    """Closed loop on the kinematic plant with the launch-file parameters: the robot follows the sine path."""
+    summary, lines = _run_harness("--model", model, "--launch", "--K", "4096", "--T", "15", "--cycles", "60", *extra)
+    assert summary["cycles"] == 60 and len(lines) == 60
+    assert summary["rmse_m"] < 0.25, summary
+    assert summary["final_x"] > 3.0, summary  # it actually drives along the path
+    # the reference's four-call cycle and the CUDA-graph path give the same controls as solve()
+    a, _ = _run_harness("--model", model, "--launch", "--K", "2048", "--T", "15", "--cycles", "5", "--quiet", *extra)
+    b, _ = _run_harness("--model", model, "--launch", "--K", "2048", "--T", "15", "--cycles", "5", "--quiet", "--split", *extra)
+    c, _ = _run_harness("--model", model, "--launch", "--K", "2048", "--T", "15", "--cycles", "5", "--quiet", "--graph", *extra)
+    assert a["final_x"] == b["final_x"] == c["final_x"] and a["rmse_m"] == b["rmse_m"] == c["rmse_m"]
