@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "libmppi_b200.so")  # env: tuning builds only
 
 MPPI_OK = 0
 MPPI_ERR_INVALID, MPPI_ERR_CUDA, MPPI_ERR_STATE, MPPI_ERR_NCCL, MPPI_ERR_ALLOC = -1, -2, -3, -4, -5

@@ -54,16 +54,32 @@ __device__ __forceinline__ float min3f(float a, float b, float c) {
   return r;
 }
 
+// shared-memory accesses by 32-bit shared-window address: no generic->shared conversion in the inner loop
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(unsigned addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32_volatile(unsigned addr) {  // ring slots are rewritten by cp.async
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // min over the window pairs [q0, q0 + 2*n2) of min(d2, best); pairs = {x0, x1, y0, y1}.  Two pairs (four window
 // points) per iteration; scanning a few points more than the candidate range is always safe (they are window
 // points too), so the range is rounded up instead of predicated.
-__device__ __forceinline__ float scan_pairs(const float4 *__restrict__ pairs, int q0, int n2, float x, float y,
-                                            float best) {
+__device__ __forceinline__ float scan_pairs(unsigned pairs_s, int q0, int n2, float x, float y, float best) {
   const u64 xx = pack2(x, x), yy = pack2(y, y);
-  const float4 *p = pairs + q0;
+  unsigned p = pairs_s + (unsigned)q0 * 16u;
 #pragma unroll 1
-  for (int k = 0; k < n2; ++k, p += 2) {
-    const float4 a = p[0], b = p[1];
+  for (int k = 0; k < n2; ++k, p += 32u) {
+    const float4 a = lds128(p), b = lds128(p + 16u);
     float a0, a1, b0, b1;
     unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
     unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
@@ -76,28 +92,27 @@ __device__ __forceinline__ float scan_pairs(const float4 *__restrict__ pairs, in
 struct GridView {
   const uint32_t *cells;  // [ny][nx]: first pair | (number of 2-pair iterations) << 16
   float inv_h, cx, cy;    // cell index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy))
-  int nx, ny;
+  unsigned nx, ny;
   int all_n2;             // iterations that cover the whole (padded) window
 };
 
 // Exact min_j min(d2(p, r_j), 1e4) over the whole window.
-__device__ __forceinline__ float min_dist2_grid(const GridView &g, const float4 *__restrict__ pairs, float x, float y) {
-  const int ix = __float2int_rd(fmaf(x, g.inv_h, g.cx));
-  const int iy = __float2int_rd(fmaf(y, g.inv_h, g.cy));
+__device__ __forceinline__ float min_dist2_grid(const GridView &g, unsigned pairs_s, float x, float y) {
+  const unsigned ix = (unsigned)__float2int_rd(fmaf(x, g.inv_h, g.cx));
+  const unsigned iy = (unsigned)__float2int_rd(fmaf(y, g.inv_h, g.cy));
   int q0 = 0, n2 = g.all_n2;
-  if ((unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny) {
-    const uint32_t e = __ldg(g.cells + (unsigned)(iy * g.nx + ix));
+  if (ix < g.nx && iy < g.ny) {
+    const uint32_t e = __ldg(g.cells + (iy * g.nx + ix));
     q0 = (int)(e & 0xFFFFu);
     n2 = (int)(e >> 16);
   }
-  return scan_pairs(pairs, q0, n2, x, y, kDist2Cap);
+  return scan_pairs(pairs_s, q0, n2, x, y, kDist2Cap);
 }
 
 // 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, so the normals of future control
 // steps stream in behind the arithmetic without ever blocking a register scoreboard
-__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async_f32(unsigned smem_dst, const float *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -106,6 +121,11 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 constexpr int kRing = 4;  // ring of control steps in flight per thread (prefetch distance: two iterations)
+
+template <int J>
+struct SlotC {
+  static constexpr int value = J;
+};
 
 }  // namespace
 
@@ -222,8 +242,11 @@ size_t pruned_smem_bytes(int T, int planes, int U) {
   return sizeof(float4) * (size_t)((T + 1) / 2 + 1) + sizeof(float) * ((size_t)kRing * U * 128 + (size_t)planes + 2 * U);
 }
 
+#ifndef MPPI_K2_MINBLOCKS
+#define MPPI_K2_MINBLOCKS 1
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
     rollout_cost_pruned_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ eps,
                                const float *__restrict__ nominal, const float *__restrict__ window,
                                const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
@@ -256,7 +279,15 @@ __global__ void __launch_bounds__(128)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float c = 0.f;
   if (i < K) {
-    const GridView gv{cells + (size_t)robot * max_cells, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx, s_gh.ny, (NP + 1) / 2};
+    const uint32_t *cp = cells + (size_t)robot * max_cells;
+    asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
+    const GridView gv{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, (unsigned)s_gh.nx, (unsigned)s_gh.ny, (NP + 1) / 2};
+    unsigned pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
+    unsigned ring_s = (unsigned)__cvta_generic_to_shared(s_eps + threadIdx.x);
+    unsigned nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
+    // pin the three shared-window addresses in registers (otherwise they are re-derived from SR_CgaCtaId per step)
+    asm volatile("" : "+r"(pairs_s), "+r"(ring_s), "+r"(nom_s));
+    constexpr unsigned kSlotBytes = U * 128 * 4;
     const float *st = state + (size_t)robot * 8;
     const int steps = T - 1;
     // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
@@ -274,35 +305,32 @@ __global__ void __launch_bounds__(128)
       hi[u] = sP.u_max[u];
     }
     CostAcc acc;
-    float cur[U], nxt[U];
+    float ca[U], cb[U];  // controls of the current and the next step (roles alternate, no register moves)
     // normals of control step t: eps[(t*U + u)*Kp + i], streamed through this thread's column of the ring
     const size_t step_stride = (size_t)U * Kp;
     const float *e_ptr = eps + (size_t)robot * planes * Kp + i;
-    float *ring = s_eps + threadIdx.x;
-    int t_issue = 0;
-    auto issue = [&]() {  // start the copy of step t_issue (nothing past the last step), one commit group per step
-      if (t_issue < steps) {
-        float *dst = ring + (t_issue % kRing) * (U * 128);
+    // start the copy of step t into ring slot `slot` (nothing past the last step); one commit group per step
+    auto issue = [&](int t, unsigned slot) {
+      if (t < steps) {
+        const unsigned dst = ring_s + slot * kSlotBytes;
 #pragma unroll
-        for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 128, e_ptr + (size_t)u * Kp);
+        for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 512u, e_ptr + (size_t)u * Kp);
         e_ptr += step_stride;
       }
       cp_async_commit();
-      ++t_issue;
     };
-    auto make = [&](int t, float *dst) {  // sampling (D5); past the last step the result is never used
-      const float *src = ring + (t % kRing) * (U * 128);
+    // sampling (D5) of step t from ring slot `slot`; past the last step the result is never used (s_nom is padded)
+    auto make = [&](int t, unsigned slot, float *dst) {
+      const unsigned src = ring_s + slot * kSlotBytes;
+      const unsigned nom = nom_s + (unsigned)(t * U) * 4u;
 #pragma unroll
-      for (int u = 0; u < U; ++u) dst[u] = sample_control(src[u * 128], sigma, s_nom[t * U + u], lo[u], hi[u]);
+      for (int u = 0; u < U; ++u)
+        dst[u] = sample_control(lds32_volatile(src + u * 512u), sigma, lds32(nom + u * 4u), lo[u], hi[u]);
       if (steer_off) dst[2] = 0.f;  // FB:517
     };
-#pragma unroll
-    for (int k = 0; k < kRing; ++k) issue();
-    cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
-    make(0, cur);
-    make(1, nxt);
-    for (int t = 0; t < n_iter; ++t) {
-      acc.path += min_dist2_grid(gv, s_pairs, x, y);
+    // one iteration: cost terms of state t, then the Euler step with the controls `cur` (next step's in `nxt`)
+    auto advance = [&](const float *cur, const float *nxt) {
+      acc.path += min_dist2_grid(gv, pairs_s, x, y);
       const float dv = cur[0] - v_ref;
       acc.vel = fmaf(dv, dv, acc.vel);
       if (MODEL == kFullBody) {
@@ -319,14 +347,43 @@ __global__ void __launch_bounds__(128)
         roll = fmaf(cur[3], dt, roll);
         pitch = fmaf(cur[4], dt, pitch);
       }
+    };
 #pragma unroll
-      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
-      // step t+2 was issued two iterations ago (slot (t+2) % kRing); the slot of step t+4 held step t, consumed
-      issue();
+    for (int k = 0; k < kRing; ++k) issue(k, (unsigned)k);
+    cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
+    make(0, 0u, ca);
+    make(1, 1u, cb);
+    // Iteration t consumes step t (cur) and t+1 (nxt), then refills: step t+4 goes into slot t%4 (held step t,
+    // consumed), step t+2 -- issued two iterations ago -- is sampled from slot (t+2)%4 into the register set that
+    // held step t.  Unrolled by the ring size so that slots and register roles are compile-time constants.
+    int t = 0;
+    for (; t + kRing <= n_iter; t += kRing) {
+      advance(ca, cb);
+      issue(t + 4, 0u);
       cp_async_wait<2>();
-      make(t + 2, nxt);
+      make(t + 2, 2u, ca);
+      advance(cb, ca);
+      issue(t + 5, 1u);
+      cp_async_wait<2>();
+      make(t + 3, 3u, cb);
+      advance(ca, cb);
+      issue(t + 6, 2u);
+      cp_async_wait<2>();
+      make(t + 4, 0u, ca);
+      advance(cb, ca);
+      issue(t + 7, 3u);
+      cp_async_wait<2>();
+      make(t + 5, 1u, cb);
     }
-    if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, s_pairs, x, y);  // state T-1: path term only (D1)
+    for (; t < n_iter; ++t) {  // at most kRing - 1 iterations; (ca, cb) = (step t, step t+1) on entry
+      advance(ca, cb);
+      issue(t + 4, (unsigned)(t & 3));
+      cp_async_wait<2>();
+#pragma unroll
+      for (int u = 0; u < U; ++u) ca[u] = cb[u];
+      make(t + 2, (unsigned)((t + 2) & 3), cb);
+    }
+    if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, pairs_s, x, y);  // state T-1: path term only (D1)
     c = combine_cost(sP, acc, MODEL == kFullBody ? st[2] - st[5] : 0.f);
     cost[(size_t)robot * K + i] = c;
   }
