@@ -329,9 +329,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    win_stride = (2 * T + 3) // 4 * 4
-    h2d = 256 + 4 * R * (win_stride + 8 + (T - 1) * U)
-    d2h = 4 * R * ((T - 1) * U + 4)
+    h2d, d2h = ctl.io_bytes()
     e2e = {"value": steps_per_solve * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps}
 

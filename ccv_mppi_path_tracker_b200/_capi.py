@@ -13,6 +13,7 @@ MPPI_ERR_INVALID, MPPI_ERR_CUDA, MPPI_ERR_STATE, MPPI_ERR_NCCL, MPPI_ERR_ALLOC =
 MODEL_DIFF_DRIVE, MODEL_STEERING, MODEL_FULL_BODY = 0, 1, 2
 DEBUG_NONE, DEBUG_NEAREST = 0, 1
 SCAN_AUTO, SCAN_LITERAL, SCAN_PRUNED = 0, 1, 2
+WINDOW_AUTO, WINDOW_HOST, WINDOW_DEVICE = 0, 1, 2
 COMM_ID_BYTES = 128
 
 
@@ -37,6 +38,7 @@ SYMBOLS = {
     "mppi_set_params": (C.c_int, [C.c_void_p, _P(MppiParams)]),
     "mppi_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "mppi_set_scan_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppi_set_window_builder": (C.c_int, [C.c_void_p, C.c_int]),
     "mppi_set_path": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double), C.c_int]),
     "mppi_set_window": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),
     "mppi_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -58,6 +60,7 @@ SYMBOLS = {
     "mppi_get_record": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
     "mppi_get_info": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
     "mppi_time_kernels": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
+    "mppi_get_io_bytes": (C.c_int, [C.c_void_p, _P(C.c_size_t), _P(C.c_size_t)]),
     "mppi_last_launch_count": (C.c_int, [C.c_void_p]),
     "mppi_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "mppi_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -113,6 +113,9 @@ class _MPPIBase:
     def set_scan_mode(self, mode):
         self._check(self.lib.mppi_set_scan_mode(self._h, mode))
 
+    def set_window_builder(self, mode):
+        self._check(self.lib.mppi_set_window_builder(self._h, mode))
+
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.mppi_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
@@ -196,6 +199,12 @@ class _MPPIBase:
         self._check(self.lib.mppi_time_kernels(self._h, int(n_iters), _fptr(ms)))
         names = ("noise", "rollout_cost", "weights", "weighted_controls", "finalize", "merge", "total", "candidate_grid")
         return dict(zip(names, (float(v) for v in ms)))
+
+    def io_bytes(self):
+        """(host->device, device->host) bytes moved by one solve()."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.mppi_get_io_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         return self.lib.mppi_last_launch_count(self._h)

@@ -84,6 +84,16 @@ struct mppi_handle_s {
   std::vector<double> window;  // [R][T][3]
   std::vector<int> cur_index;
   bool have_inputs = false, have_nominal = false;
+  // device-side window builder (many-robot handles)
+  int window_builder = MPPI_WINDOW_AUTO;
+  bool paths_dirty = false;
+  double *d_path = nullptr;
+  int *d_path_off = nullptr;
+  unsigned char *d_win_fixed = nullptr;
+  size_t d_path_capacity = 0;
+  size_t state64_off = 0;
+  std::vector<double> last_state;  // [R][S] pose of the last staged solve (mppi_get_window)
+  double last_dt = 0.0;
   bool external_noise = false;
   int debug_flags = 0, scan_mode = MPPI_SCAN_AUTO;
   uint64_t seed = 0x5EED0000ull;
@@ -125,8 +135,39 @@ void invalidate_graphs(mppi_handle h) {
   h->exec_kernels = h->exec_solve = nullptr;
 }
 
+bool device_windows(mppi_handle h) {
+  return h->window_builder == MPPI_WINDOW_DEVICE || (h->window_builder == MPPI_WINDOW_AUTO && h->R >= 8);
+}
+
+// (re)upload all robots' paths, concatenated, when any of them changed
+int flush_paths(mppi_handle h) {
+  if (!h->paths_dirty) return MPPI_OK;
+  std::vector<int> off(h->R + 1, 0);
+  for (int r = 0; r < h->R; ++r) off[r + 1] = off[r] + (int)(h->path[r].size() / 2);
+  std::vector<double> all((size_t)2 * off[h->R] + 2, 0.0);
+  for (int r = 0; r < h->R; ++r)
+    if (!h->path[r].empty()) memcpy(all.data() + (size_t)2 * off[r], h->path[r].data(), sizeof(double) * h->path[r].size());
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (all.size() > h->d_path_capacity) {
+    invalidate_graphs(h);  // the buffer address is a kernel argument of the captured window node
+    if (h->d_path) cudaFree(h->d_path);
+    h->d_path = nullptr;
+    h->d_path_capacity = all.size() + all.size() / 4;
+    CU_TRY(h, cudaMalloc((void **)&h->d_path, sizeof(double) * h->d_path_capacity));
+    h->d.path_xy = h->d_path;
+  }
+  CU_TRY(h, cudaMemcpy(h->d_path, all.data(), sizeof(double) * all.size(), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->d_path_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->d_win_fixed, h->window_fixed.data(), (size_t)h->R, cudaMemcpyHostToDevice));
+  h->paths_dirty = false;
+  return MPPI_OK;
+}
+
 void fill_header(mppi_handle h, double dt) {
   SolveHeader *hd = reinterpret_cast<SolveHeader *>(h->h_in);
+  hd->v_ref64 = h->params.v_ref;
+  hd->dt64 = dt;
+  hd->resolution64 = h->params.resolution;
   hd->P = make_solve_params(h->model, h->T, h->params, dt);
   hd->inv_lambda = (float)(1.0 / h->params.lambda);
   hd->key0 = (uint32_t)h->seed;
@@ -147,6 +188,10 @@ int effective_scan(mppi_handle h, bool *want_nearest) {
 int issue_kernels(mppi_handle h, cudaStream_t s) {
   const DeviceState &d = h->d;
   int n = 0;
+  if (device_windows(h)) {
+    CU_TRY(h, launch_window_builder(d, s));
+    ++n;
+  }
   if (h->external_noise) CU_TRY(h, launch_reset_cmin(d, s));
   else CU_TRY(h, launch_noise(d, s));
   ++n;
@@ -195,16 +240,28 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
   float *win = reinterpret_cast<float *>(h->h_in + kHeaderBytes);
   float *st = win + (size_t)d.R * d.win_stride;
   float *nom = reinterpret_cast<float *>(h->h_in + h->nominal_off);
+  double *st64 = reinterpret_cast<double *>(h->h_in + h->state64_off);
+  const bool on_device = device_windows(h);
+  if (on_device) {
+    rc = flush_paths(h);
+    if (rc) return rc;
+  }
+  memcpy(h->last_state.data(), state, sizeof(double) * (size_t)h->R * h->S);
+  h->last_dt = dt;
   for (int r = 0; r < h->R; ++r) {
     const double *s = state + (size_t)r * h->S;
     double *w = h->window.data() + (size_t)r * h->T * 3;
     if (!h->window_fixed[r]) {
       if (h->path[r].empty()) return fail(h, MPPI_ERR_STATE, "no path or window set for robot " + std::to_string(r));
-      h->cur_index[r] = calc_ref_path(h->path[r].data(), (int)(h->path[r].size() / 2), s[0], s[1], h->params.v_ref,
-                                      dt, h->params.resolution, h->T, w);
+      if (!on_device)
+        h->cur_index[r] = calc_ref_path(h->path[r].data(), (int)(h->path[r].size() / 2), s[0], s[1], h->params.v_ref,
+                                        dt, h->params.resolution, h->T, w);
     }
-    window_to_robot_frame(w, h->T, s[0], s[1], win + (size_t)r * d.win_stride);
-    state_to_robot_frame(h->model, s, w[2], st + (size_t)r * 8);
+    // windows built on the device (K-1) overwrite this robot's slot after the H2D copy
+    if (!on_device || h->window_fixed[r]) window_to_robot_frame(w, h->T, s[0], s[1], win + (size_t)r * d.win_stride);
+    state_to_robot_frame(h->model, s, st + (size_t)r * 8);
+    st64[2 * r] = s[0];
+    st64[2 * r + 1] = s[1];
   }
   if (u_nominal) {
     const size_t n = (size_t)h->R * d.planes;
@@ -289,7 +346,10 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.win_stride = (int)align_up((size_t)2 * horizon, 4);
   d.rec_stride = (int)align_up((size_t)4 + d.planes, 4);
   d.nb3 = (num_samples + kWeightBlock * 4 - 1) / (kWeightBlock * 4);
-  d.nchunk = (d.Kp + kReduceChunk - 1) / kReduceChunk;
+  {
+    const int chunk = kReduceChunk / reduce_planes_per_block(d.Kp);
+    d.nchunk = (d.Kp + chunk - 1) / chunk;
+  }
   d.n_ranks = 1;
   // candidate grid of the pruned scan: building it costs ~cells*T distance evaluations per robot and solve, the
   // rollouts K*T*(~100 instr): keep the grid below a few per cent of that
@@ -318,7 +378,8 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   const size_t st_bytes = sizeof(float) * (size_t)d.R * 8;
   const size_t nom_bytes = sizeof(float) * (size_t)d.R * d.planes;
   h->nominal_off = align_up(kHeaderBytes + win_bytes + st_bytes, 16);
-  h->in_bytes = align_up(h->nominal_off + nom_bytes, 16);
+  h->state64_off = align_up(h->nominal_off + nom_bytes, 16);
+  h->in_bytes = align_up(h->state64_off + sizeof(double) * 2 * (size_t)d.R, 16);
   h->out_bytes = sizeof(float) * ((size_t)d.R * d.planes + (size_t)d.R * 4);
   CU_NEW(cudaMallocHost((void **)&h->h_in, h->in_bytes));
   CU_NEW(cudaMallocHost((void **)&h->h_out, h->out_bytes));
@@ -332,6 +393,15 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.window = reinterpret_cast<float *>(h->d_in + kHeaderBytes);
   d.state = d.window + (size_t)d.R * d.win_stride;
   d.nominal = reinterpret_cast<float *>(h->d_in + h->nominal_off);
+  d.state64 = reinterpret_cast<double *>(h->d_in + h->state64_off);
+  CU_NEW(cudaMalloc((void **)&h->d_path_off, sizeof(int) * ((size_t)d.R + 1)));
+  CU_NEW(cudaMemset(h->d_path_off, 0, sizeof(int) * ((size_t)d.R + 1)));
+  CU_NEW(cudaMalloc((void **)&h->d_win_fixed, (size_t)d.R));
+  CU_NEW(cudaMemset(h->d_win_fixed, 0, (size_t)d.R));
+  CU_NEW(cudaMalloc((void **)&d.cur_index, sizeof(int) * (size_t)d.R));
+  CU_NEW(cudaMemset(d.cur_index, 0, sizeof(int) * (size_t)d.R));
+  d.path_off = h->d_path_off;
+  d.win_fixed = h->d_win_fixed;
   d.u_new = h->d_out;
   d.stats = h->d_out + (size_t)d.R * d.planes;
   CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
@@ -353,6 +423,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   h->window_fixed.assign(n_robots, 0);
   h->window.assign((size_t)n_robots * horizon * 3, 0.0);
   h->cur_index.assign(n_robots, 0);
+  h->last_state.assign((size_t)n_robots * h->S, 0.0);
   *out = h;
   return MPPI_OK;
 }
@@ -368,6 +439,7 @@ int mppi_destroy(mppi_handle h) {
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
   cudaFree(d.record); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
   cudaFree(d.grid_hdr); cudaFree(d.grid_cells);
+  cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -405,11 +477,21 @@ int mppi_set_scan_mode(mppi_handle h, int scan_mode) {
   return MPPI_OK;
 }
 
+int mppi_set_window_builder(mppi_handle h, int mode) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (mode < MPPI_WINDOW_AUTO || mode > MPPI_WINDOW_DEVICE) return fail(h, MPPI_ERR_INVALID, "unknown window builder mode");
+  if (mode != h->window_builder) invalidate_graphs(h);
+  h->window_builder = mode;
+  h->paths_dirty = true;
+  return MPPI_OK;
+}
+
 int mppi_set_path(mppi_handle h, int robot, const double *path_xy, int n_points) {
   if (!h) return MPPI_ERR_INVALID;
   if (robot < 0 || robot >= h->R || n_points < 1 || !path_xy) return fail(h, MPPI_ERR_INVALID, "bad robot index or empty path");
   h->path[robot].assign(path_xy, path_xy + (size_t)2 * n_points);
   h->window_fixed[robot] = 0;
+  h->paths_dirty = true;
   return MPPI_OK;
 }
 
@@ -419,6 +501,7 @@ int mppi_set_window(mppi_handle h, int robot, const double *window_xyyaw) {
   memcpy(h->window.data() + (size_t)robot * h->T * 3, window_xyyaw, sizeof(double) * 3 * (size_t)h->T);
   h->window_fixed[robot] = 1;
   h->cur_index[robot] = 0;
+  h->paths_dirty = true;
   return MPPI_OK;
 }
 
@@ -486,8 +569,10 @@ int mppi_upload(mppi_handle h, const double *state, double dt, const double *u_n
   CU_TRY(h, cudaSetDevice(h->device));
   int rc = stage_inputs(h, state, dt, u_nominal);
   if (rc) return rc;
-  const size_t bytes = u_nominal ? h->in_bytes : h->nominal_off;
-  CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, u_nominal ? h->in_bytes : h->nominal_off, cudaMemcpyHostToDevice, h->stream));
+  if (!u_nominal)  // keep the device-resident warm start: skip the nominal slot, copy the FP64 poses behind it
+    CU_TRY(h, cudaMemcpyAsync(h->d_in + h->state64_off, h->h_in + h->state64_off, h->in_bytes - h->state64_off,
+                              cudaMemcpyHostToDevice, h->stream));
   CU_TRY(h, cudaEventRecord(h->staged, h->stream));
   h->staged_pending = true;
   h->have_inputs = true;
@@ -602,6 +687,17 @@ int mppi_get_noise(mppi_handle h, int robot, float *eps) {
 int mppi_get_window(mppi_handle h, int robot, double *window_xyyaw, int *current_index) {
   if (!h) return MPPI_ERR_INVALID;
   if (robot < 0 || robot >= h->R) return fail(h, MPPI_ERR_INVALID, "bad robot index");
+  if (device_windows(h) && !h->window_fixed[robot] && !h->path[robot].empty() && h->last_dt > 0.0) {
+    // built on the device: current_index_ comes back from there, the FP64 window is re-derived from it with the
+    // host form of calc_RefPath (same expressions)
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    int cur = 0;
+    CU_TRY(h, cudaMemcpy(&cur, h->d.cur_index + robot, sizeof(int), cudaMemcpyDeviceToHost));
+    h->cur_index[robot] = cur;
+    window_from_index(h->path[robot].data(), (int)(h->path[robot].size() / 2), cur, h->params.v_ref, h->last_dt,
+                      h->params.resolution, h->T, h->window.data() + (size_t)robot * h->T * 3);
+  }
   if (window_xyyaw) memcpy(window_xyyaw, h->window.data() + (size_t)robot * h->T * 3, sizeof(double) * 3 * (size_t)h->T);
   if (current_index) *current_index = h->cur_index[robot];
   return MPPI_OK;
@@ -640,6 +736,13 @@ int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int
   return MPPI_OK;
 }
 
+int mppi_get_io_bytes(mppi_handle h, size_t *h2d_bytes, size_t *d2h_bytes) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (h2d_bytes) *h2d_bytes = h->in_bytes;
+  if (d2h_bytes) *d2h_bytes = h->out_bytes;
+  return MPPI_OK;
+}
+
 int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
   if (!h) return MPPI_ERR_INVALID;
   if (n_iters < 1 || !ms) return fail(h, MPPI_ERR_INVALID, "n_iters >= 1 and ms != NULL required");
@@ -654,6 +757,7 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
   const int scan = effective_scan(h, &want_nearest);
   int rc = MPPI_OK;
   for (int it = 0; it <= n_iters && rc == MPPI_OK; ++it) {
+    if (device_windows(h)) launch_window_builder(d, s);
     cudaEventRecord(ev[0], s);
     if (h->external_noise) launch_reset_cmin(d, s); else launch_noise(d, s);
     cudaEventRecord(ev[1], s);

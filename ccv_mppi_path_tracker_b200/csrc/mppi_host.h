@@ -60,10 +60,10 @@ inline int current_index(const double *path_xy, int n, double px, double py) {
   return index;
 }
 
-// calc_RefPath: DD:156-181.  window = T x {x_ref, y_ref, yaw_ref}; yaw_ref[T-1] = 0 (never written, DD:44).
-inline int calc_ref_path(const double *path_xy, int n, double px, double py, double v_ref, double dt,
-                         double resolution, int T, double *window) {
-  const int cur = current_index(path_xy, n, px, py);
+// calc_RefPath after get_CurrentIndex: DD:160-181.  window = T x {x_ref, y_ref, yaw_ref}; yaw_ref[T-1] = 0 (never
+// written, DD:44).
+inline void window_from_index(const double *path_xy, int n, int cur, double v_ref, double dt, double resolution, int T,
+                              double *window) {
   const double step = v_ref * dt / resolution;  // DD:160
   for (int i = 0; i < T; ++i) {
     int index = (int)(cur + i * step);  // DD:163 truncation of a double
@@ -78,6 +78,13 @@ inline int calc_ref_path(const double *path_xy, int n, double px, double py, dou
   for (int i = 0; i + 1 < T; ++i)
     window[3 * i + 2] = atan2(window[3 * (i + 1) + 1] - window[3 * i + 1], window[3 * (i + 1)] - window[3 * i]);
   if (T > 0) window[3 * (T - 1) + 2] = 0.0;
+}
+
+// calc_RefPath: DD:156-181
+inline int calc_ref_path(const double *path_xy, int n, double px, double py, double v_ref, double dt,
+                         double resolution, int T, double *window) {
+  const int cur = current_index(path_xy, n, px, py);
+  window_from_index(path_xy, n, cur, v_ref, dt, resolution, T, window);
   return cur;
 }
 
@@ -90,15 +97,14 @@ inline void window_to_robot_frame(const double *window, int T, double px, double
   }
 }
 
-// state record {0, 0, yaw, roll, pitch, yaw_ref0, 0, 0}
-inline void state_to_robot_frame(int model, const double *state, double yaw_ref0, float *out) {
+// state record {0, 0, yaw, roll, pitch, 0, 0, 0}  (yaw_ref_[0] is derived from the FP32 window by the kernels)
+inline void state_to_robot_frame(int model, const double *state, float *out) {
   out[0] = 0.f;
   out[1] = 0.f;
   out[2] = (float)state[2];
   out[3] = model == kFullBody ? (float)state[3] : 0.f;
   out[4] = model == kFullBody ? (float)state[4] : 0.f;
-  out[5] = (float)yaw_ref0;
-  out[6] = out[7] = 0.f;
+  out[5] = out[6] = out[7] = 0.f;
 }
 
 }  // namespace mppi

@@ -16,7 +16,9 @@ struct SolveHeader {
   uint32_t key0, key1;    // Philox key = 64-bit seed (informational; K1 takes the key as a kernel argument)
   uint32_t robot_offset;  // global index of robot 0 of this handle
   uint32_t q_offset;      // global sample offset of this shard / 4
-  uint32_t pad[3];
+  uint32_t pad[2];
+  // FP64 inputs of the device-side window builder (get_CurrentIndex + calc_RefPath, DD:126-181)
+  double v_ref64, dt64, resolution64;
 };
 
 // geometry of one robot's candidate grid (written by K0, read by K2): cell (ix, iy) = floor(fma(x, inv_h, cx)), ...
@@ -28,6 +30,7 @@ struct GridHeader {
 // HBM layout owned by one handle.  R robots, K samples (this shard), T horizon, U controls, P = (T-1)*U planes.
 //   inbuf    one allocation, one H2D copy per solve:
 //     hdr      SolveHeader (padded to 256 B)
+//     state64  [R][2]    pose x, y in FP64 (device-side window builder only; after nominal)
 //     window   [R][WS]   WS floats: T x {x_ref - x0, y_ref - y0} (robot-centred frame, FP32), padded to 16 B
 //     state    [R][8]    {0, 0, yaw, roll, pitch, yaw_ref[0], -, -}
 //     nominal  [R][P]    warm start u*; the merge kernel overwrites it in place with the new controls
@@ -57,6 +60,12 @@ struct DeviceState {
   unsigned int *cmin = nullptr;
   uint32_t *counter = nullptr;
   int *nearest = nullptr;
+  // device-side window builder (K-1): all robots' paths concatenated, FP64
+  const double *path_xy = nullptr;   // [sum n_r][2]
+  const int *path_off = nullptr;     // [R + 1]
+  const double *state64 = nullptr;   // [R][2] pose x, y (in inbuf)
+  const unsigned char *win_fixed = nullptr;  // [R] 1 = window given by mppi_set_window (host-built), skip
+  int *cur_index = nullptr;          // [R] current_index_ of the last solve
   GridHeader *grid_hdr = nullptr;
   uint32_t *grid_cells = nullptr;
   int grid_max_cells = 0;
@@ -75,6 +84,8 @@ cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
 cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s);
+// K-1 get_CurrentIndex + calc_RefPath on the device, one CTA per robot (many-robot handles; FP64 like the host path)
+cudaError_t launch_window_builder(const DeviceState &d, cudaStream_t s);
 // K0  candidate grid of the pruned scan, once per robot and solve (mppi_rollout_pruned.cu)
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s);
 // K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
@@ -82,6 +93,8 @@ cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s);
 bool pruned_scan_supported(int T, int planes);
 // K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
+// planes per block of K4 (1, 2 or 4) and the matching number of sample chunks: nchunk = ceil(Kp / (4096 / ppb))
+int reduce_planes_per_block(int Kp);
 // K4  weighted control reduction partials
 cudaError_t launch_weighted_controls(const DeviceState &d, cudaStream_t s);
 // K5  fixed-order final sums -> record;  K6 merge of G records -> u_new, nominal, stats, counter++

@@ -112,6 +112,32 @@ MPPI_HD void sincos_f32(float a, float &s, float &c) {
   c = ((q + 1u) & 2u) ? -co : co;
 }
 
+// atan2 in the FP32 contract (same bits on host and device): octant reduction + the classic single-precision
+// arctangent polynomial on [0, tan(pi/8)]; |error| < 3e-7 rad.  atan2_f32(0, 0) = 0 like atan2 (duplicate window
+// points, DD:175-178).  Used for yaw_ref_[0] of the full-body yaw term (FB:408), evaluated on the robot-centred
+// FP32 window; non-finite inputs are not specified.
+MPPI_HD float atan2_f32(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+  float a = mx > 0.f ? mn / mx : 0.f;  // in [0, 1]
+  float base = 0.f;
+  if (a > 0.4142135623730950f) {  // tan(pi/8)
+    base = 0.7853981633974483f;
+    a = (a - 1.0f) / (a + 1.0f);
+  }
+  const float z = a * a;
+  float p = fmaf(z, 8.05374449538e-2f, -1.38776856032e-1f);
+  p = fmaf(p, z, 1.99777106478e-1f);
+  p = fmaf(p, z, -3.33329491539e-1f);
+  float r = base + fmaf(p * z, a, a);
+  if (ay > ax) r = 1.5707963267948966f - r;
+  if (x < 0.f) r = 3.141592653589793f - r;
+  return y < 0.f ? -r : r;
+}
+
+// yaw_ref_[0] = atan2(y_ref[1] - y_ref[0], x_ref[1] - x_ref[0]) (DD:175-178) from the FP32 window
+MPPI_HD float yaw_ref0_f32(float x0, float y0, float x1, float y1) { return atan2_f32(y1 - y0, x1 - x0); }
+
 // squared distance of calc_MinDistance's inner expression (DD:188) without the sqrt
 MPPI_HD float dist2(float x, float y, float xr, float yr) {
   float dx = x - xr;
@@ -197,7 +223,7 @@ MPPI_HD float combine_cost(const SolveParams &P, const CostAcc &a, float yaw0_er
 //   Win::x(j)/y(j)  -> window point j, robot-centred frame
 //   Sink::state(t, x, y, yaw, roll, pitch), Sink::nearest(t, j, d2), Sink::control(t, u, value),
 //   Sink::zmp(t, zx, zy)  -> debug taps, no-ops in the production kernel
-// state0 = {0, 0, yaw, roll, pitch} in the robot-centred frame; yaw_ref0 = yaw_ref_[0] of the window.
+// state0 = {0, 0, yaw, roll, pitch} in the robot-centred frame; yaw_ref0 = yaw_ref0_f32 of the window (T >= 2).
 template <int MODEL, typename Eps, typename Nom, typename Win, typename Sink>
 MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, float yaw_ref0, const Eps &eps,
                                    const Nom &nom, const Win &win, Sink &sink) {

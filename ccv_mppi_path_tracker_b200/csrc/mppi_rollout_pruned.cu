@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
       make(t + 2, (unsigned)((t + 2) & 3), cb);
     }
     if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, pairs_s, x, y);  // state T-1: path term only (D1)
-    c = combine_cost(sP, acc, MODEL == kFullBody ? st[2] - st[5] : 0.f);
+    float yaw0_err = 0.f;
+    if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
+      const float4 w01 = s_pairs[0];
+      yaw0_err = st[2] - yaw_ref0_f32(w01.x, w01.z, w01.y, w01.w);
+    }
+    c = combine_cost(sP, acc, yaw0_err);
     cost[(size_t)robot * K + i] = c;
   }
   block_min_to_global(c, i < K, cmin + robot, s_red);

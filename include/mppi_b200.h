@@ -77,6 +77,15 @@ typedef enum {
   MPPI_SCAN_PRUNED = 2
 } mppi_scan_mode;
 
+/* Where get_CurrentIndex + calc_RefPath (DD:126-181) run for robots that have a path: on the host inside
+ * mppi_upload (FP64), or in a device kernel, one CTA per robot (FP64, same expressions; for many-robot handles).
+ * AUTO = DEVICE when n_robots >= 8. */
+typedef enum {
+  MPPI_WINDOW_AUTO = 0,
+  MPPI_WINDOW_HOST = 1,
+  MPPI_WINDOW_DEVICE = 2
+} mppi_window_builder;
+
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
 
 /* Replaces the constructors' allocation of sample[K], optimal_solution, window and weights_ (DD:36-46,
@@ -93,6 +102,7 @@ int mppi_abi_version(void);
 int mppi_set_params(mppi_handle h, const mppi_params *params);
 int mppi_set_debug(mppi_handle h, int debug_flags);
 int mppi_set_scan_mode(mppi_handle h, int scan_mode);
+int mppi_set_window_builder(mppi_handle h, int mode);
 
 /* ---- inputs -------------------------------------------------------------------------------------------- */
 
@@ -155,6 +165,8 @@ int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int
  * pruned scan (0 when the literal scan runs).  Advances the warm start and the solve counter like n_iters + 1
  * calls of mppi_enqueue. */
 int mppi_time_kernels(mppi_handle h, int n_iters, float *ms /* [8] */);
+/* bytes one mppi_solve moves: host -> device (header, windows, states, warm start) and device -> host (controls, stats) */
+int mppi_get_io_bytes(mppi_handle h, size_t *h2d_bytes, size_t *d2h_bytes);
 /* number of kernel launches issued by the last mppi_enqueue (bench.py's gpu_launches claim) */
 int mppi_last_launch_count(mppi_handle h);
 

@@ -70,6 +70,8 @@ def _load_twin():
         lib.twin_rollout_cost.argtypes = [C.c_int, _P(OracleParams), C.c_int, C.c_int, _P(C.c_double), C.c_double,
                                           _P(C.c_double), _P(C.c_float), _P(C.c_double), _P(C.c_float), _P(C.c_int),
                                           _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_float)]
+        lib.twin_atan2.restype = None
+        lib.twin_atan2.argtypes = [_P(C.c_float), _P(C.c_float), C.c_int, _P(C.c_float)]
         lib.twin_sincos.restype = None
         lib.twin_sincos.argtypes = [_P(C.c_float), C.c_int, _P(C.c_float), _P(C.c_float)]
         _twin = lib
@@ -206,3 +208,12 @@ def twin_sincos(a):
     c = np.zeros_like(a)
     lib.twin_sincos(_f(a), a.size, _f(s), _f(c))
     return s, c
+
+
+def twin_atan2(y, x):
+    lib = _load_twin()
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros_like(y)
+    lib.twin_atan2(_f(y), _f(x), y.size, _f(out))
+    return out

@@ -86,7 +86,8 @@ int twin_rollout_cost(int model, const mppi_params *p, int K, int T, const doubl
   std::vector<float> win(2 * (size_t)T), nom((size_t)(T - 1) * P.U);
   float st[8];
   window_to_robot_frame(window, T, state[0], state[1], win.data());
-  state_to_robot_frame(model, state, window[2], st);
+  state_to_robot_frame(model, state, st);
+  st[5] = yaw_ref0_f32(win[0], win[1], win[2], win[3]);  // what the kernels derive from the same FP32 window
   for (size_t k = 0; k < nom.size(); ++k) nom[k] = (float)u_nominal[k];
   switch (model) {
     case kDiffDrive: run<kDiffDrive>(P, K, st, st[5], win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
@@ -94,6 +95,10 @@ int twin_rollout_cost(int model, const mppi_params *p, int K, int T, const doubl
     default: run<kFullBody>(P, K, st, st[5], win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
   }
   return 0;
+}
+
+void twin_atan2(const float *y, const float *x, int n, float *out) {
+  for (int i = 0; i < n; ++i) out[i] = atan2_f32(y[i], x[i]);
 }
 
 void twin_sincos(const float *a, int n, float *s, float *c) {

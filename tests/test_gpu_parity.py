@@ -417,3 +417,45 @@ def test_cpp_harness_tracks_the_launch_path(model, extra):
     b, _ = _run_harness("--model", model, "--launch", "--K", "2048", "--T", "15", "--cycles", "5", "--quiet", "--split", *extra)
     c, _ = _run_harness("--model", model, "--launch", "--K", "2048", "--T", "15", "--cycles", "5", "--quiet", "--graph", *extra)
     assert a["final_x"] == b["final_x"] == c["final_x"] and a["rmse_m"] == b["rmse_m"] == c["rmse_m"]
+
+
+# ---- device-side window builder (get_CurrentIndex + calc_RefPath per robot in a kernel) ------------------------
+
+def test_device_window_builder_equals_host_builder():
+    """Many-robot handles build every robot's window on the device (FP64, the reference's expressions): same
+    current index, same window, bit-identical costs and controls as the host-built windows -- including robots
+    past the end of their path (tail clamp), far from it (index 0) and on the 1-point data.csv path."""
+    K, T, R = 256, 50, 12
+    case = make_case("diff_drive", K, T)
+    rng = np.random.default_rng(12)
+    states = np.zeros((R, 3))
+    path_sets = []
+    for r in range(R):
+        pth = paths.sin_path(course_length=10.0, A1=1.0, omega1=0.25, delta1=2 * np.pi * r / R, delta2=0.0, delta3=0.0)
+        if r == 3:
+            pth = np.array([[-5.45606, -6.61448]])
+        j = (9 * r) % pth.shape[0]
+        states[r, :2] = pth[j] + 0.1 * rng.standard_normal(2)
+        states[r, 2] = 0.3 * rng.standard_normal()
+        path_sets.append(pth)
+    states[5, :2] = path_sets[5][-2] + [0.02, 0.01]   # near the end: the window clamps to the last pose
+    states[7, :2] = [400.0, -250.0]                   # farther than 100 m from everything: index 0
+    eps = rng.standard_normal((R, T - 1, K, 2)).astype(np.float32)
+    out = {}
+    for mode in (_capi.WINDOW_HOST, _capi.WINDOW_DEVICE):
+        with _make_ctl(case, n_robots=R) as ctl:
+            ctl.set_window_builder(mode)
+            for r in range(R):
+                ctl.set_path(path_sets[r], robot=r)
+            ctl.set_noise(eps)
+            u = ctl.solve(states, case["dt"]).copy()
+            u2 = ctl.solve(states + 0.05, case["dt"]).copy()  # second cycle: poses moved, windows rebuilt
+            out[mode] = (u, u2, [ctl.costs(r) for r in range(R)], [ctl.window(r) for r in range(R)])
+    h, d = out[_capi.WINDOW_HOST], out[_capi.WINDOW_DEVICE]
+    assert np.array_equal(h[0], d[0]) and np.array_equal(h[1], d[1])
+    for r in range(R):
+        assert np.array_equal(h[2][r].view(np.uint32), d[2][r].view(np.uint32))
+        assert h[3][r][1] == d[3][r][1] and np.array_equal(h[3][r][0], d[3][r][0])
+        w_or, c_or = oracle.calc_ref_path(path_sets[r], states[r, 0] + 0.05, states[r, 1] + 0.05, case["sp"]["v_ref"],
+                                          case["dt"], case["sp"]["resolution"], T)
+        assert d[3][r][1] == c_or and np.array_equal(d[3][r][0], w_or)

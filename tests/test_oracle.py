@@ -135,3 +135,13 @@ def test_twin_sincos_accuracy():
     s, c = oracle.twin_sincos(a)
     assert np.abs(s - np.sin(a.astype(np.float64))).max() < 3e-7
     assert np.abs(c - np.cos(a.astype(np.float64))).max() < 3e-7
+
+
+def test_twin_atan2_accuracy():
+    rng = np.random.default_rng(0)
+    y = np.concatenate([rng.normal(0, 1, 100000), [0.0, 0.0, 1.0, -1.0, 0.0, 1e-30, 3.0]]).astype(np.float32)
+    x = np.concatenate([rng.normal(0, 1, 100000), [0.0, 1.0, 0.0, 0.0, -1.0, 1e-30, -3.0]]).astype(np.float32)
+    a = oracle.twin_atan2(y, x)
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert np.abs(a - ref).max() < 4e-7
+    assert a[100000] == 0.0  # atan2(0, 0) = 0: duplicate window points (DD:175-178)
