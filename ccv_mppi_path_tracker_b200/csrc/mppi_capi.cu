@@ -99,6 +99,9 @@ struct mppi_handle_s {
   uint64_t seed = 0x5EED0000ull;
   int64_t sample_offset = 0, k_global = 0;
   int robot_offset = 0;
+  // K0 (candidate grid) runs beside K1 (noise): they are independent
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // graphs
   bool use_graph = false;
   cudaGraphExec_t exec_kernels = nullptr, exec_solve = nullptr;
@@ -134,6 +137,10 @@ void invalidate_graphs(mppi_handle h) {
   if (h->exec_solve) cudaGraphExecDestroy(h->exec_solve);
   h->exec_kernels = h->exec_solve = nullptr;
 }
+
+// K5 + K6 as one launch (one block per robot): unsharded handles whose partial arrays are small (latency path,
+// many-robot handles); large-K handles keep the wide finalize + merge pair
+bool fused_tail(mppi_handle h) { return h->n_ranks == 1 && (long long)h->d.planes * h->d.nchunk <= 4096; }
 
 bool device_windows(mppi_handle h) {
   return h->window_builder == MPPI_WINDOW_DEVICE || (h->window_builder == MPPI_WINDOW_AUTO && h->R >= 8);
@@ -192,21 +199,31 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
     CU_TRY(h, launch_window_builder(d, s));
     ++n;
   }
+  bool want_nearest;
+  const int scan = effective_scan(h, &want_nearest);
+  if (scan == MPPI_SCAN_PRUNED) {  // fork: the candidate grid (needs only the window) beside the noise generator
+    CU_TRY(h, cudaEventRecord(h->ev_fork, s));
+    CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    CU_TRY(h, launch_candidate_grid(d, h->side_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+    ++n;
+  }
   if (h->external_noise) CU_TRY(h, launch_reset_cmin(d, s));
   else CU_TRY(h, launch_noise(d, s));
   ++n;
-  bool want_nearest;
-  const int scan = effective_scan(h, &want_nearest);
-  if (scan == MPPI_SCAN_PRUNED) {
-    CU_TRY(h, launch_candidate_grid(d, s));
-    ++n;
-  }
+  if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
   CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, s));
   ++n;
   CU_TRY(h, launch_weights(d, s));
   ++n;
   CU_TRY(h, launch_weighted_controls(d, s));
   ++n;
+  if (fused_tail(h)) {
+    CU_TRY(h, launch_finalize_merge(d, s));
+    ++n;
+    h->launch_count = n;
+    return MPPI_OK;
+  }
   CU_TRY(h, launch_finalize(d, s));
   ++n;
   if (h->n_ranks > 1) {
@@ -373,6 +390,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CU_NEW(cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming));
+  CU_NEW(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 
   const size_t win_bytes = sizeof(float) * (size_t)d.R * d.win_stride;
   const size_t st_bytes = sizeof(float) * (size_t)d.R * 8;
@@ -432,6 +452,7 @@ int mppi_destroy(mppi_handle h) {
   if (!h) return MPPI_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->side_stream) cudaStreamSynchronize(h->side_stream);
   invalidate_graphs(h);
   if (h->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(h->comm);
   DeviceState &d = h->d;
@@ -444,6 +465,9 @@ int mppi_destroy(mppi_handle h) {
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->staged) cudaEventDestroy(h->staged);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return MPPI_OK;
@@ -769,12 +793,15 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     cudaEventRecord(ev[3], s);
     launch_weighted_controls(d, s);
     cudaEventRecord(ev[4], s);
-    launch_finalize(d, s);
+    const bool fused = fused_tail(h);
+    if (fused) launch_finalize_merge(d, s); else launch_finalize(d, s);
     cudaEventRecord(ev[5], s);
-    if (h->n_ranks > 1 &&
-        g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
-      rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
-    launch_merge(d, s);
+    if (!fused) {
+      if (h->n_ranks > 1 &&
+          g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
+        rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
+      launch_merge(d, s);
+    }
     cudaEventRecord(ev[6], s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));

@@ -100,6 +100,8 @@ cudaError_t launch_weighted_controls(const DeviceState &d, cudaStream_t s);
 // K5  fixed-order final sums -> record;  K6 merge of G records -> u_new, nominal, stats, counter++
 cudaError_t launch_finalize(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge(const DeviceState &d, cudaStream_t s);
+// K5 + K6 in one launch when the handle is not sharded (identical results)
+cudaError_t launch_finalize_merge(const DeviceState &d, cudaStream_t s);
 
 // ordered-uint encoding so that atomicMin(unsigned) orders floats (negative costs included)
 MPPI_HD uint32_t float_to_ordered(float f) {
