@@ -12,7 +12,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall
 HOSTFP    := -ffp-contract=off -mfma
 REF       ?= /root/reference
 
-all: lib oracle harness
+all: lib oracle harness hosttest
 
 lib: $(LIB)
 $(LIB): $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_rollout_pruned.cu $(CSRC)/mppi_device.cuh $(CSRC)/mppi_capi.cu $(CSRC)/mppi_kernels.h $(CSRC)/mppi_math.h $(CSRC)/mppi_host.h $(CSRC)/philox.h include/mppi_b200.h
@@ -22,6 +22,10 @@ $(LIB): $(CSRC)/mppi_kernels.cu $(CSRC)/mppi_rollout_pruned.cu $(CSRC)/mppi_devi
 harness: $(PKG)/mppi_harness
 $(PKG)/mppi_harness: $(CSRC)/host/mppi_harness.cpp $(CSRC)/host/controllers.hpp $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ $(CSRC)/host/mppi_harness.cpp -L$(PKG) -lmppi_b200 -Wl,-rpath,'$$ORIGIN'
+
+hosttest: tests/host/fb_monitor_check
+tests/host/fb_monitor_check: tests/host/fb_monitor_check.cpp $(CSRC)/host/controllers.hpp include/mppi_b200.h
+	$(CXX) -O1 -std=c++17 -ffp-contract=off -Wall -o $@ tests/host/fb_monitor_check.cpp -L$(PKG) -lmppi_b200 -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 
 oracle: oracle/liboracle.so oracle/libtwin.so
 oracle/liboracle.so: oracle/mppi_oracle.c oracle/mppi_oracle.h
@@ -36,4 +40,4 @@ ref:
 clean:
 	rm -f $(LIB) $(PKG)/mppi_harness oracle/*.so oracle/_ref/* $(CSRC)/ptxas.log
 
-.PHONY: all lib oracle ref harness clean
+.PHONY: all lib oracle ref harness hosttest clean

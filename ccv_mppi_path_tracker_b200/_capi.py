@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "libmppi_b200.
 MPPI_OK = 0
 MPPI_ERR_INVALID, MPPI_ERR_CUDA, MPPI_ERR_STATE, MPPI_ERR_NCCL, MPPI_ERR_ALLOC = -1, -2, -3, -4, -5
 MODEL_DIFF_DRIVE, MODEL_STEERING, MODEL_FULL_BODY = 0, 1, 2
-DEBUG_NONE, DEBUG_NEAREST = 0, 1
+DEBUG_NONE, DEBUG_NEAREST, DEBUG_STATES = 0, 1, 2
 SCAN_AUTO, SCAN_LITERAL, SCAN_PRUNED = 0, 1, 2
 WINDOW_AUTO, WINDOW_HOST, WINDOW_DEVICE = 0, 1, 2
 COMM_ID_BYTES = 128
@@ -54,6 +54,7 @@ SYMBOLS = {
     "mppi_get_costs": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
     "mppi_get_weights": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
     "mppi_get_nearest": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int32)]),
+    "mppi_get_states": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),
     "mppi_get_noise": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
     "mppi_get_window": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double), _P(C.c_int)]),
     "mppi_get_stats": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),

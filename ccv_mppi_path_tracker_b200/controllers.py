@@ -171,6 +171,26 @@ class _MPPIBase:
         self._check(self.lib.mppi_get_nearest(self._h, robot, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
+    def states(self, robot=0):
+        """Candidate trajectories [K][T][S] (world frame) of the last solve; needs set_debug(DEBUG_STATES)."""
+        out = np.empty((self.num_samples_, self.horizon_, self.S), dtype=np.float64)
+        self._check(self.lib.mppi_get_states(self._h, robot, _dptr(out)))
+        return out
+
+    def optimal_path(self, robot=0):
+        """publish_OptimalPath (DD:295-312): optimal_solution re-rolled from the current pose with predict_NextState,
+        in double on the host like the reference; returns [T][3] (x, y, yaw)."""
+        T = self.horizon_
+        st = np.zeros((T, 3))
+        st[0] = self.current_state[robot, :3]
+        u = self.optimal_solution[robot]
+        for t in range(T - 1):
+            heading = st[t, 2] if self.MODEL == "diff_drive" else st[t, 2] + u[t, 2]
+            st[t + 1, 0] = st[t, 0] + u[t, 0] * np.cos(heading) * self.dt_
+            st[t + 1, 1] = st[t, 1] + u[t, 0] * np.sin(heading) * self.dt_
+            st[t + 1, 2] = st[t, 2] + u[t, 1] * self.dt_
+        return st
+
     def noise(self, robot=0):
         out = np.empty((self.horizon_ - 1, self.num_samples_, self.U), dtype=np.float32)
         self._check(self.lib.mppi_get_noise(self._h, robot, _fptr(out)))
@@ -227,6 +247,58 @@ class SteeringDiffDriveMPPI(_MPPIBase):
 class FullBodyMPPI(_MPPIBase):
     """class FullBodyMPPI (full_body_mppi.h:68): controls (v, w, direction, roll_v, pitch_v), ZMP cost."""
     MODEL = "full_body"
+
+    # the node's ZMP monitors (topics zmp_y / true_zmp, full_body_mppi.cpp:628-633); host-side, not inputs of the solve
+    MASS, BODY_H, BODY_D, BODY_W, ALPHA = 60.0, 0.8075, 0.208, 0.208, 0.3  # full_body_mppi.h:213-218
+    CONTACTS = np.array([[0.0, 0.225, 0.075], [0.0, -0.225, 0.075], [0.245, 0.167, -0.003], [0.245, -0.167, -0.004],
+                         [-0.245, -0.167, -0.004], [-0.245, 0.167, -0.003]])  # full_body_mppi.cpp:57-63
+
+    def reset_monitors(self):
+        self.zmp_x_, self.zmp_y_ = 0.0, 0.0
+        self.true_ZMP = np.zeros(3)
+        self.last_HG = np.zeros(3)
+
+    def computeZMPfromModel(self, CoM, accel, HGdot):
+        """full_body_mppi.cpp:597-603"""
+        g = np.array([0.0, 0.0, -9.8])
+        z = np.array([0.0, 0.0, 1.0])
+        M_O = np.cross(CoM, self.MASS * g) - np.cross(CoM, self.MASS * np.asarray(accel)) - np.asarray(HGdot)
+        return np.cross(z, M_O) / (self.MASS * np.dot(g - np.asarray(accel), z))
+
+    def update_model_zmp(self, imu_roll, imu_pitch, accel_x, accel_y, omega, dt=None):
+        """The ZMP part of get_CurrentState (full_body_mppi.cpp:551-566): low-passed model ZMP."""
+        if not hasattr(self, "last_HG"):
+            self.reset_monitors()
+        dt = self.dt_ if dt is None else dt
+        m, b = self.MASS, self.BODY_H / 2
+        I = np.array([(m * (self.BODY_W ** 2 + self.BODY_H ** 2)) / 12 + m * b * b,
+                      (m * (self.BODY_H ** 2 + self.BODY_D ** 2)) / 12 + m * b * b,
+                      (m * (self.BODY_D ** 2 + self.BODY_W ** 2)) / 12])
+        CoM = np.array([b * np.sin(imu_pitch), -b * np.sin(imu_roll), b * np.cos(imu_pitch) * np.cos(imu_roll)])
+        HG = I * np.asarray(omega, dtype=np.float64)
+        HGdot = (HG - self.last_HG) / dt
+        self.last_HG = HG
+        Z = self.computeZMPfromModel(CoM, [accel_x, accel_y, 0.0], HGdot)
+        self.zmp_x_ = self.ALPHA * Z[0] + (1 - self.ALPHA) * self.zmp_x_
+        self.zmp_y_ = self.ALPHA * Z[1] + (1 - self.ALPHA) * self.zmp_y_
+        return self.zmp_x_, self.zmp_y_
+
+    def calc_true_ZMP(self, forces):
+        """full_body_mppi.cpp:568-596: forces [6][3] (wheels l, r, casters fl, fr, bl, br) in the base frame."""
+        if not hasattr(self, "true_ZMP"):
+            self.reset_monitors()
+        f = np.asarray(forces, dtype=np.float64).reshape(6, 3)
+        sumF, sumM = np.zeros(3), np.zeros(3)
+        for r, fi in zip(self.CONTACTS, f):
+            if fi[2] > 0.0:
+                sumF += fi
+                sumM += np.cross(r, fi)
+        n = np.array([0.0, 0.0, 1.0])
+        denom = np.dot(sumF, n)
+        if abs(denom) < 1e-6:
+            return self.true_ZMP
+        self.true_ZMP = self.ALPHA * (np.cross(n, sumM) / denom) + (1 - self.ALPHA) * self.true_ZMP
+        return self.true_ZMP
 
 
 CONTROLLERS = {"diff_drive": DiffDriveMPPI, "steering": SteeringDiffDriveMPPI, "full_body": FullBodyMPPI}

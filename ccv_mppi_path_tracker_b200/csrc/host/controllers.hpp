@@ -154,6 +154,19 @@ class MPPIBase {
   void determine_OptimalSolution() { enqueue_once(); check(mppi_download(h_, optimal_solution.u.data())); }
 
   CmdVel cmd_vel() const { return CmdVel{optimal_solution.at(0, 0), optimal_solution.at(0, 1)}; }  // DD:248-253
+  // publish_OptimalPath (DD:295-312): optimal_solution re-rolled from the current pose with predict_NextState, in
+  // double on the host like the reference; returns T x {x, y, yaw}
+  std::vector<double> optimal_path() const {
+    std::vector<double> st((size_t)horizon_ * 3, 0.0);
+    st[0] = state_[0]; st[1] = state_[1]; st[2] = state_[2];
+    for (int t = 0; t + 1 < horizon_; ++t) {
+      const double heading = U_ == 2 ? st[3 * t + 2] : st[3 * t + 2] + optimal_solution.at(t, 2);
+      st[3 * (t + 1)] = st[3 * t] + optimal_solution.at(t, 0) * cos(heading) * dt_;
+      st[3 * (t + 1) + 1] = st[3 * t + 1] + optimal_solution.at(t, 0) * sin(heading) * dt_;
+      st[3 * (t + 1) + 2] = st[3 * t + 2] + optimal_solution.at(t, 1) * dt_;
+    }
+    return st;
+  }
   virtual CmdPos cmd_pos() const = 0;
 
   std::vector<float> costs() const {
@@ -286,6 +299,70 @@ class FullBodyMPPI : public MPPIBase {
   // get_CurrentState (FB:528-566): pose + IMU roll / pitch
   void set_state(double x, double y, double yaw, double roll, double pitch) {
     state_[0] = x; state_[1] = y; state_[2] = yaw; state_[3] = roll; state_[4] = pitch;
+  }
+
+  // ---- the node's ZMP monitors (published on zmp_y / true_zmp, FB:628-633; not inputs of the solve) -------------
+  // constants: FBh:213-216 body box + mass, FB:86-91 base2CoM = height / 2 and I_O, FBh:30 gravity_, FBh:218 alpha
+  double mass = 60.0, upper_body_height = 0.8075, upper_body_depth = 0.208, upper_body_width = 0.208, alpha = 0.3;
+  double zmp_x_ = 0.0, zmp_y_ = 0.0;        // current_state_.zmp_x_[0], zmp_y_[0] (low-passed model ZMP)
+  double true_ZMP[3] = {0.0, 0.0, 0.0};     // force-sensor ZMP (low-passed)
+  double last_HG[3] = {0.0, 0.0, 0.0};
+
+  // computeZMPfromModel (FB:597-603)
+  void computeZMPfromModel(const double CoM[3], const double accel[3], const double HGdot[3], double out[3]) const {
+    const double g[3] = {0.0, 0.0, -9.8};
+    double mg[3], ma[3], c1[3], c2[3], MO[3];
+    for (int k = 0; k < 3; ++k) { mg[k] = mass * g[k]; ma[k] = mass * accel[k]; }
+    cross(CoM, mg, c1);
+    cross(CoM, ma, c2);
+    for (int k = 0; k < 3; ++k) MO[k] = c1[k] - c2[k] - HGdot[k];
+    const double z[3] = {0.0, 0.0, 1.0};
+    double zx[3];
+    cross(z, MO, zx);
+    const double denom = mass * ((g[0] - accel[0]) * z[0] + (g[1] - accel[1]) * z[1] + (g[2] - accel[2]) * z[2]);
+    for (int k = 0; k < 3; ++k) out[k] = zx[k] / denom;
+  }
+  // the ZMP part of get_CurrentState (FB:551-566): IMU attitude, base-frame acceleration and angular velocity in,
+  // low-passed model ZMP out.  Call once per cycle after set_state().
+  void update_model_zmp(double imu_roll, double imu_pitch, double accel_x, double accel_y, const double omega[3]) {
+    const double b = upper_body_height / 2;
+    const double I[3] = {(mass * (upper_body_width * upper_body_width + upper_body_height * upper_body_height)) / 12 + mass * b * b,
+                         (mass * (upper_body_height * upper_body_height + upper_body_depth * upper_body_depth)) / 12 + mass * b * b,
+                         (mass * (upper_body_depth * upper_body_depth + upper_body_width * upper_body_width)) / 12};
+    const double CoM[3] = {b * sin(imu_pitch), -b * sin(imu_roll), b * cos(imu_pitch) * cos(imu_roll)};
+    const double accel[3] = {accel_x, accel_y, 0.0};
+    double HG[3], HGdot[3], Z[3];
+    for (int k = 0; k < 3; ++k) {
+      HG[k] = I[k] * omega[k];
+      HGdot[k] = (HG[k] - last_HG[k]) / dt_;
+      last_HG[k] = HG[k];
+    }
+    computeZMPfromModel(CoM, accel, HGdot, Z);
+    zmp_x_ = alpha * Z[0] + (1 - alpha) * zmp_x_;
+    zmp_y_ = alpha * Z[1] + (1 - alpha) * zmp_y_;
+  }
+  // calc_true_ZMP (FB:568-596): six contact forces (wheels l, r, casters fl, fr, bl, br) in the base frame
+  void calc_true_ZMP(const double forces[6][3]) {
+    static const double pos[6][3] = {{0.0, 0.225, 0.075},     {0.0, -0.225, 0.075},   {0.245, 0.167, -0.003},
+                                     {0.245, -0.167, -0.004}, {-0.245, -0.167, -0.004}, {-0.245, 0.167, -0.003}};  // FB:58-64
+    double sumF[3] = {0, 0, 0}, sumM[3] = {0, 0, 0};
+    for (int i = 0; i < 6; ++i)
+      if (forces[i][2] > 0.0) {
+        double m[3];
+        cross(pos[i], forces[i], m);
+        for (int k = 0; k < 3; ++k) { sumF[k] += forces[i][k]; sumM[k] += m[k]; }
+      }
+    const double n[3] = {0.0, 0.0, 1.0};
+    const double denom = sumF[0] * n[0] + sumF[1] * n[1] + sumF[2] * n[2];
+    if (fabs(denom) < 1e-6) return;  // FB:588-592
+    double num[3];
+    cross(n, sumM, num);
+    for (int k = 0; k < 3; ++k) true_ZMP[k] = alpha * (num[k] / denom) + (1 - alpha) * true_ZMP[k];
+  }
+  static void cross(const double a[3], const double b[3], double out[3]) {
+    out[0] = a[1] * b[2] - a[2] * b[1];
+    out[1] = a[2] * b[0] - a[0] * b[2];
+    out[2] = a[0] * b[1] - a[1] * b[0];
   }
   CmdPos cmd_pos() const override {  // FB:246-275
     CmdPos c;

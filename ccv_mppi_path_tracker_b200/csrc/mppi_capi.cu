@@ -184,10 +184,12 @@ void fill_header(mppi_handle h, double dt) {
 }
 
 // which nearest-point scan the next solve runs: the literal kernel is the one that records argmin indices
-int effective_scan(mppi_handle h, bool *want_nearest) {
+int effective_scan(mppi_handle h, bool *want_nearest, bool *want_states = nullptr) {
   *want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && h->d.nearest;
+  const bool ws = (h->debug_flags & MPPI_DEBUG_STATES) && h->d.states_dbg;
+  if (want_states) *want_states = ws;
   int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
-  if (*want_nearest || !pruned_scan_supported(h->d.T, h->d.planes)) scan = MPPI_SCAN_LITERAL;
+  if (*want_nearest || ws || !pruned_scan_supported(h->d.T, h->d.planes)) scan = MPPI_SCAN_LITERAL;
   return scan;
 }
 
@@ -199,8 +201,8 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
     CU_TRY(h, launch_window_builder(d, s));
     ++n;
   }
-  bool want_nearest;
-  const int scan = effective_scan(h, &want_nearest);
+  bool want_nearest, want_states;
+  const int scan = effective_scan(h, &want_nearest, &want_states);
   if (scan == MPPI_SCAN_PRUNED) {  // fork: the candidate grid (needs only the window) beside the noise generator
     CU_TRY(h, cudaEventRecord(h->ev_fork, s));
     CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
@@ -212,7 +214,7 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
   else CU_TRY(h, launch_noise(d, s));
   ++n;
   if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, s));
+  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, s));
   ++n;
   CU_TRY(h, launch_weights(d, s));
   ++n;
@@ -459,7 +461,7 @@ int mppi_destroy(mppi_handle h) {
   if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
   cudaFree(d.record); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
-  cudaFree(d.grid_hdr); cudaFree(d.grid_cells);
+  cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg);
   cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
@@ -487,6 +489,11 @@ int mppi_set_debug(mppi_handle h, int debug_flags) {
     const size_t bytes = sizeof(int) * (size_t)h->R * h->K * h->T;
     CU_TRY(h, cudaMalloc((void **)&h->d.nearest, bytes));
     CU_TRY(h, cudaMemset(h->d.nearest, 0xFF, bytes));
+  }
+  if ((debug_flags & MPPI_DEBUG_STATES) && !h->d.states_dbg) {
+    const size_t bytes = sizeof(float) * (size_t)h->R * h->K * h->T * 5;
+    CU_TRY(h, cudaMalloc((void **)&h->d.states_dbg, bytes));
+    CU_TRY(h, cudaMemset(h->d.states_dbg, 0, bytes));
   }
   if (debug_flags != h->debug_flags) invalidate_graphs(h);
   h->debug_flags = debug_flags;
@@ -692,6 +699,31 @@ int mppi_get_nearest(mppi_handle h, int robot, int32_t *nearest) {
   return MPPI_OK;
 }
 
+int mppi_get_states(mppi_handle h, int robot, double *states) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (robot < 0 || robot >= h->R || !states) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
+  if (!(h->debug_flags & MPPI_DEBUG_STATES) || !h->d.states_dbg)
+    return fail(h, MPPI_ERR_STATE, "mppi_get_states needs mppi_set_debug(MPPI_DEBUG_STATES) before the solve");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)h->K * h->T;
+  std::vector<float> raw(n * 5);
+  CU_TRY(h, cudaMemcpy(raw.data(), h->d.states_dbg + (size_t)robot * n * 5, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost));
+  // back to the world frame: the kernels work robot-centred
+  const double px = h->last_state[(size_t)robot * h->S], py = h->last_state[(size_t)robot * h->S + 1];
+  for (size_t k = 0; k < n; ++k) {
+    double *o = states + k * h->S;
+    o[0] = (double)raw[5 * k] + px;
+    o[1] = (double)raw[5 * k + 1] + py;
+    o[2] = raw[5 * k + 2];
+    if (h->S == 5) {
+      o[3] = raw[5 * k + 3];
+      o[4] = raw[5 * k + 4];
+    }
+  }
+  return MPPI_OK;
+}
+
 int mppi_get_noise(mppi_handle h, int robot, float *eps) {
   if (!h) return MPPI_ERR_INVALID;
   if (robot < 0 || robot >= h->R || !eps) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
@@ -787,7 +819,7 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     cudaEventRecord(ev[1], s);
     if (scan == MPPI_SCAN_PRUNED) launch_candidate_grid(d, s);
     cudaEventRecord(ev[7], s);
-    launch_rollout_cost(d, scan, want_nearest, s);
+    launch_rollout_cost(d, scan, want_nearest, false, s);
     cudaEventRecord(ev[2], s);
     launch_weights(d, s);
     cudaEventRecord(ev[3], s);

@@ -60,6 +60,7 @@ struct DeviceState {
   unsigned int *cmin = nullptr;
   uint32_t *counter = nullptr;
   int *nearest = nullptr;
+  float *states_dbg = nullptr;  // [R][K][T][5] predicted states, debug only (MPPI_DEBUG_STATES)
   // device-side window builder (K-1): all robots' paths concatenated, FP64
   const double *path_xy = nullptr;   // [sum n_r][2]
   const int *path_off = nullptr;     // [R + 1]
@@ -83,7 +84,8 @@ cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
 // used instead of K1 when the caller supplied the noise tensor (mppi_set_noise)
 cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
-cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, cudaStream_t s);
+cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, bool write_states,
+                                cudaStream_t s);
 // K-1 get_CurrentIndex + calc_RefPath on the device, one CTA per robot (many-robot handles; FP64 like the host path)
 cudaError_t launch_window_builder(const DeviceState &d, cudaStream_t s);
 // K0  candidate grid of the pruned scan, once per robot and solve (mppi_rollout_pruned.cu)

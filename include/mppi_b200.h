@@ -64,7 +64,8 @@ typedef struct mppi_handle_s *mppi_handle;
 /* Optional per-solve debug taps (all device->host copies happen only when requested). */
 typedef enum {
   MPPI_DEBUG_NONE = 0,
-  MPPI_DEBUG_NEAREST = 1 /* keep nearest window index per (sample, t): the implicit argmin of DD:186-190 */
+  MPPI_DEBUG_NEAREST = 1, /* keep nearest window index per (sample, t): the implicit argmin of DD:186-190 */
+  MPPI_DEBUG_STATES = 2   /* keep every predicted state: what publish_CandidatePath shows (DD:265-294) */
 } mppi_debug_flags;
 
 /* Implementation of the nearest-window-point scan inside the fused rollout+cost kernel. Both are exact and
@@ -154,6 +155,8 @@ int mppi_use_graph(mppi_handle h, int enable);
 int mppi_get_costs(mppi_handle h, int robot, float *cost /* [K] */);
 int mppi_get_weights(mppi_handle h, int robot, float *weights /* [K], exp(-(c-c_min)/lambda), not normalised */);
 int mppi_get_nearest(mppi_handle h, int robot, int32_t *nearest /* [K][T], needs MPPI_DEBUG_NEAREST */);
+/* candidate trajectories sample[i].x_, y_, yaw_ [, roll_, pitch_] (DD:287-288), world frame; needs MPPI_DEBUG_STATES */
+int mppi_get_states(mppi_handle h, int robot, double *states /* [K][T][S] */);
 int mppi_get_noise(mppi_handle h, int robot, float *eps /* [T-1][K][U] */);
 int mppi_get_window(mppi_handle h, int robot, double *window_xyyaw /* [T][3] */, int *current_index);
 /* stats[0] = c_min, stats[1] = sum of shifted weights, stats[2] = effective sample size (global when sharded) */

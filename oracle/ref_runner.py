@@ -58,3 +58,17 @@ def run(model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
         out["zmp"] = take(K * max(T - 2, 0) * 2).reshape(K, max(T - 2, 0), 2)
     out["current_index"] = int(take(1, np.int32)[0])
     return out
+
+
+def run_estimator(cycles):
+    """cycles: [n][30] doubles {dt, imu_roll, imu_pitch, accel_x, accel_y, omega[3], forces[6][3], x, y, yaw, 0};
+    returns [n][5] {zmp_x, zmp_y, true_ZMP xyz} from the reference's calc_true_ZMP() + get_CurrentState()."""
+    cycles = np.ascontiguousarray(cycles, dtype=np.float64).reshape(-1, 30)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<i", cycles.shape[0]))
+            f.write(cycles.tobytes())
+        subprocess.run([os.path.join(_HERE, "_ref", BIN["full_body"]), "--estimator", fin, fout], check=True,
+                       stderr=subprocess.DEVNULL)
+        return np.fromfile(fout, dtype=np.float64).reshape(-1, 5)

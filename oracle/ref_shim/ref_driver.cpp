@@ -82,7 +82,59 @@ static void rd(FILE *f, T *dst, size_t n) {
   }
 }
 
+#if REF_NODE == 3
+// estimator mode: argv = --estimator in out.  in: int32 n_cycles, then per cycle 30 doubles
+// {dt, imu_roll, imu_pitch, accel_x, accel_y, omega[3], forces[6][3], pose x, y, yaw, pad}; out: per cycle 5 doubles
+// {zmp_x, zmp_y, true_ZMP x, y, z} after the reference's own calc_true_ZMP() and get_CurrentState() (FB:528-596).
+static int run_estimator(const char *fin, const char *fout) {
+  FILE *f = fopen(fin, "rb");
+  if (!f) return 1;
+  int32_t n;
+  rd(f, &n, 1);
+  std::vector<double> in((size_t)n * 30);
+  rd(f, in.data(), in.size());
+  fclose(f);
+  std::cout.setstate(std::ios_base::failbit);
+  ref_shim::param_table()["horizon"] = 3;
+  ref_shim::param_table()["num_samples"] = 1;
+  Node node;
+  static const char *topics[6] = {"/left_force_sensor/raw",       "/right_force_sensor/raw",     "/front_left_force_sensor/raw",
+                                  "/front_right_force_sensor/raw", "/back_left_force_sensor/raw", "/back_right_force_sensor/raw"};
+  FILE *o = fopen(fout, "wb");
+  for (int c = 0; c < n; ++c) {
+    const double *v = in.data() + (size_t)c * 30;
+    node.dt_ = v[0];
+    node.imu_roll_ = v[1];
+    node.imu_pitch_ = v[2];
+    node.accel_x = v[3];
+    node.accel_y = v[4];
+    node.filterd_imu_.angular_velocity.x = v[5];
+    node.filterd_imu_.angular_velocity.y = v[6];
+    node.filterd_imu_.angular_velocity.z = v[7];
+    for (int k = 0; k < 6; ++k) {
+      node.force_sensor_data_[topics[k]].wrench.force.x = v[8 + 3 * k];
+      node.force_sensor_data_[topics[k]].wrench.force.y = v[9 + 3 * k];
+      node.force_sensor_data_[topics[k]].wrench.force.z = v[10 + 3 * k];
+    }
+    node.use_gazebo_pose_ = true;
+    node.gazebo_pose_.pose.position.x = v[26];
+    node.gazebo_pose_.pose.position.y = v[27];
+    node.gazebo_pose_.pose.orientation = tf::createQuaternionMsgFromYaw(v[28]);
+    node.calc_true_ZMP();
+    node.get_CurrentState();
+    double out[5] = {node.current_state_.zmp_x_[0], node.current_state_.zmp_y_[0], node.true_ZMP.x(), node.true_ZMP.y(),
+                     node.true_ZMP.z()};
+    fwrite(out, 8, 5, o);
+  }
+  fclose(o);
+  return 0;
+}
+#endif
+
 int main(int argc, char **argv) {
+#if REF_NODE == 3
+  if (argc >= 4 && std::string(argv[1]) == "--estimator") return run_estimator(argv[2], argv[3]);
+#endif
   if (argc < 3) return 1;
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 1;

@@ -60,5 +60,26 @@ def main():
         print(name, "cost range", r["cost"].min(), r["cost"].max(), "u_new[0]", r["u_new"][0])
 
 
+def estimator_golden():
+    """Eight cycles of the full-body node's ZMP monitors (calc_true_ZMP + get_CurrentState, FB:528-596)."""
+    rng = np.random.default_rng(77)
+    n = 8
+    cyc = np.zeros((n, 30))
+    cyc[:, 0] = rng.uniform(0.08, 0.12, n)           # dt
+    cyc[:, 1:3] = rng.normal(0, 0.08, (n, 2))        # imu roll, pitch
+    cyc[:, 3:5] = rng.normal(0, 0.6, (n, 2))         # accel x, y (base frame)
+    cyc[:, 5:8] = rng.normal(0, 0.3, (n, 3))         # angular velocity
+    forces = rng.normal(0, 5.0, (n, 6, 3))
+    forces[:, :, 2] = rng.uniform(-20, 150, (n, 6))  # some contacts unloaded (f_z <= 0 is skipped)
+    forces[3, :, 2] = -1.0                           # a cycle with no contact at all: denom ~ 0 -> estimate kept
+    cyc[:, 8:26] = forces.reshape(n, 18)
+    cyc[:, 26:29] = rng.normal(0, 1.0, (n, 3))
+    out = ref_runner.run_estimator(cyc)
+    np.savez_compressed(os.path.join(HERE, "fb_estimator.npz.dat"), cycles=cyc, ref_out=out)
+    os.replace(os.path.join(HERE, "fb_estimator.npz.dat.npz"), os.path.join(HERE, "fb_estimator.dat"))
+    print("fb_estimator", out[-1])
+
+
 if __name__ == "__main__":
+    estimator_golden()
     main()

@@ -146,3 +146,32 @@ def test_merge_partials_is_a_log_sum_exp_merge():
 def test_make_case_is_deterministic():
     a, b = make_case("steering", 64, 10, seed=3), make_case("steering", 64, 10, seed=3)
     assert np.array_equal(a["eps"], b["eps"]) and a["sp"] == b["sp"]
+
+
+def test_full_body_zmp_monitors_match_the_reference(tmp_path):
+    """f4: the full-body node's ZMP monitors (calc_true_ZMP + the ZMP part of get_CurrentState, FB:528-596) in the
+    Python and the C++ host classes against eight golden cycles of the UNMODIFIED reference node."""
+    import struct
+    import subprocess
+    from ccv_mppi_path_tracker_b200.controllers import FullBodyMPPI
+    from common import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "fb_estimator.dat"), allow_pickle=False)
+    cyc, ref = g["cycles"], g["ref_out"]
+    assert np.array_equal(ref[3, 2:], ref[2, 2:])  # the no-contact cycle keeps the previous force-sensor estimate
+    fb = FullBodyMPPI.__new__(FullBodyMPPI)  # monitors only: no device handle
+    fb.dt_ = 0.1
+    fb.reset_monitors()
+    got = []
+    for v in cyc:
+        tz = fb.calc_true_ZMP(v[8:26].reshape(6, 3)).copy()
+        zx, zy = fb.update_model_zmp(v[1], v[2], v[3], v[4], v[5:8], dt=v[0])
+        got.append([zx, zy, *tz])
+    assert np.allclose(np.array(got), ref, rtol=1e-12, atol=1e-15)
+    exe = os.path.join(ROOT, "tests", "host", "fb_monitor_check")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", ROOT, "hosttest"], check=True)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    fin.write_bytes(struct.pack("<i", cyc.shape[0]) + np.ascontiguousarray(cyc).tobytes())
+    subprocess.run([exe, str(fin), str(fout)], check=True)
+    cpp = np.fromfile(fout, dtype=np.float64).reshape(-1, 5)
+    assert np.allclose(cpp, ref, rtol=1e-12, atol=1e-15)

@@ -459,3 +459,32 @@ def test_device_window_builder_equals_host_builder():
         w_or, c_or = oracle.calc_ref_path(path_sets[r], states[r, 0] + 0.05, states[r, 1] + 0.05, case["sp"]["v_ref"],
                                           case["dt"], case["sp"]["resolution"], T)
         assert d[3][r][1] == c_or and np.array_equal(d[3][r][0], w_or)
+
+
+@pytest.mark.parametrize("model", ["diff_drive", "steering", "full_body"])
+def test_candidate_trajectories_debug_tap(model):
+    """MPPI_DEBUG_STATES: the predicted states behind publish_CandidatePath -- bit-exact against the FP32 twin
+    (robot-centred), within 5e-5 m of the FP64 oracle over the horizon."""
+    K, T = 512, 40
+    case = make_case(model, K, T, seed=4)
+    with _make_ctl(case) as ctl:
+        ctl.set_noise(case["eps"][None])
+        ctl.set_debug(_capi.DEBUG_STATES)
+        ctl.optimal_solution[0] = case["u0"]
+        ctl.solve(case["state"], case["dt"])
+        st = ctl.states()
+        window, _ = ctl.window()
+        opt = ctl.optimal_path()
+        u = ctl.optimal_solution[0].copy()
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"], want=("states",))
+    S = case["S"]
+    rel = st.copy()
+    rel[:, :, :2] -= case["state"][:2]
+    assert np.array_equal(rel[:, :, 2:].astype(np.float32), tw["states"][:, :, 2:S])
+    assert np.abs(rel[:, :, :2] - tw["states"][:, :, :2]).max() < 1e-6  # (x, y) went through a double add
+    o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"], want=("states",))
+    assert np.abs(st - o["states"]).max() < 5e-5
+    # publish_OptimalPath: the new controls without noise, through the oracle's predict_States
+    o2 = oracle.solve(model, dict(case["sp"], control_noise=0.0), 1, T, case["state"], case["dt"], case["path"],
+                      np.zeros((T - 1, 1, case["U"]), np.float32), u, want=("states",))
+    assert np.abs(opt - o2["states"][0, :, :3]).max() < 1e-12
