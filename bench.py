@@ -57,7 +57,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -298,8 +298,10 @@ def main():
     for _ in range(args.warmup):
         ctl.enqueue()
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
+    # NVML polling takes a driver lock: rank 0 only, so that 8 ranks do not slow each other's launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -308,7 +310,7 @@ def main():
     sync_all()
     ms_total = e0.elapsed_time(e1)
     launches = ctl.launch_count() * args.steps
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,8 +349,12 @@ def main():
         fl = flop_per_step(model, T)
         t_k2 = km["rollout_cost"] * 1e-3
         achieved = local_steps * fl / t_k2 / 1e12
+        # DRAM traffic of one K2 launch from the committed ncu --set full capture of this workload
+        # (profiles/r01_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
+        traffic = 838.5e6 if args.workload == "diff_drive_K1M_T100" else None
         roofline = {"bound": "fp32", "kernel": "rollout_cost", "achieved": achieved, "peak": fp32_peak_max,
-                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": traffic,
+                    "traffic_note": "bytes per launch (ncu); algorithmic bytes = 4*U per rollout-step = 830.5e6",
                     "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
                     "frac_at_observed_clock": achieved / fp32_peak_obs,
                     "algorithmic_flop_per_rollout_step": fl,
