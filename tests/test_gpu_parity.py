@@ -490,3 +490,43 @@ def test_candidate_trajectories_debug_tap(model):
     o2 = oracle.solve(model, wide, 1, T, case["state"], case["dt"], case["path"],
                       np.zeros((T - 1, 1, case["U"]), np.float32), u, want=("states",))
     assert np.abs(opt - o2["states"][0, :, :3]).max() < 1e-12
+
+
+def test_randomised_sweep_bit_exact_costs():
+    """Forty random configurations (model, K, T, dt, sigma, lambda, weights, pose, path phase, warm start): per-sample
+    costs of the production path bit-identical to the FP32 twin, controls within tolerance of the FP64 oracle."""
+    rng = np.random.default_rng(2026)
+    models = ["diff_drive", "steering", "full_body"]
+    for trial in range(40):
+        model = models[trial % 3]
+        K = int(rng.integers(1, 3000))
+        T = int(rng.integers(2, 130))
+        ov = dict(control_noise=float(rng.uniform(0.05, 1.5)), lambda_=float(rng.uniform(0.3, 5.0)),
+                  path_weight=float(rng.uniform(0.5, 20.0)), v_ref=float(rng.uniform(0.3, 2.0)))
+        if model == "full_body":
+            ov.update(roll_off=bool(rng.integers(0, 2)), steer_off=bool(rng.integers(0, 4) == 0),
+                      zmp_weight=float(rng.uniform(0, 20)), back_weight=float(rng.uniform(0, 3)))
+        case = make_case(model, K, T, seed=1000 + trial, **ov)
+        dt = float(rng.uniform(0.03, 0.25))
+        pth = paths.sin_path(course_length=float(rng.uniform(3, 25)), A1=float(rng.uniform(0, 2)),
+                             omega1=float(rng.uniform(0.05, 0.4)), delta1=float(rng.uniform(0, 6.28)), delta2=0.0, delta3=0.0)
+        state = case["state"].copy()
+        j = int(rng.integers(0, pth.shape[0]))
+        state[:2] = pth[j] + rng.normal(0, 0.4, 2)
+        state[2] = rng.normal(0, 1.0)
+        u0 = case["u0"] + rng.normal(0, 0.3, case["u0"].shape)
+        with _make_ctl(case) as ctl:
+            ctl.set_path(pth)
+            ctl.set_noise(case["eps"][None])
+            ctl.optimal_solution[0] = u0
+            u_gpu = ctl.solve(state, dt).copy()
+            cost = ctl.costs()
+            window, _ = ctl.window()
+            ess = ctl.stats()["ess"]
+        tw = oracle.twin_rollout_cost(model, case["sp"], K, T, state, dt, window, case["eps"], u0)
+        assert np.array_equal(cost.view(np.uint32), tw["cost"].view(np.uint32)), (trial, model, K, T)
+        o = oracle.solve(model, case["sp"], K, T, state, dt, pth, case["eps"], u0)
+        err = (np.abs(u_gpu - o["u_new"]) / np.where(_urange(case) > 0, _urange(case), 1)).max()
+        # cost error <= 1e-5*c perturbs a weight by <= 1e-5*c/lambda: scale the control tolerance with it
+        tol = max(U_TOL, 4e-5 * float(np.abs(o["cost"]).max()) / case["sp"]["lambda_"])
+        assert err <= tol, (trial, model, K, T, err, tol, ess)
