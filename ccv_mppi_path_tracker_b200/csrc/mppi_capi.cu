@@ -142,6 +142,9 @@ void invalidate_graphs(mppi_handle h) {
 // many-robot handles); large-K handles keep the wide finalize + merge pair
 bool fused_tail(mppi_handle h) { return h->n_ranks == 1 && (long long)h->d.planes * h->d.nchunk <= 4096; }
 
+// K3 folded into K4 (every K4 block recomputes the weights of its samples): pays off while K * planes is small
+bool fused_weights(const mppi_handle_s *h) { return h->K <= 32768; }
+
 bool device_windows(mppi_handle h) {
   return h->window_builder == MPPI_WINDOW_DEVICE || (h->window_builder == MPPI_WINDOW_AUTO && h->R >= 8);
 }
@@ -216,9 +219,11 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
   if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
   CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, s));
   ++n;
-  CU_TRY(h, launch_weights(d, s));
-  ++n;
-  CU_TRY(h, launch_weighted_controls(d, s));
+  if (!fused_weights(h)) {
+    CU_TRY(h, launch_weights(d, s));
+    ++n;
+  }
+  CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
   ++n;
   if (fused_tail(h)) {
     CU_TRY(h, launch_finalize_merge(d, s));
@@ -429,6 +434,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
   CU_NEW(cudaMalloc((void **)&d.cost, sizeof(float) * (size_t)d.R * d.K));
   CU_NEW(cudaMalloc((void **)&d.weight, sizeof(float) * (size_t)d.R * d.K));
+  if (fused_weights(h)) d.nb3 = d.nchunk;  // the partial (sum w, sum w^2) come from K4's chunks
   CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * d.nb3 * 2));
   CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.planes * d.nchunk));
   CU_NEW(cudaMalloc((void **)&d.record, sizeof(float) * (size_t)d.R * d.rec_stride));
@@ -821,9 +827,9 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     cudaEventRecord(ev[7], s);
     launch_rollout_cost(d, scan, want_nearest, false, s);
     cudaEventRecord(ev[2], s);
-    launch_weights(d, s);
+    if (!fused_weights(h)) launch_weights(d, s);
     cudaEventRecord(ev[3], s);
-    launch_weighted_controls(d, s);
+    launch_weighted_controls(d, fused_weights(h), s);
     cudaEventRecord(ev[4], s);
     const bool fused = fused_tail(h);
     if (fused) launch_finalize_merge(d, s); else launch_finalize(d, s);

@@ -97,8 +97,8 @@ bool pruned_scan_supported(int T, int planes);
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 // planes per block of K4 (1, 2 or 4) and the matching number of sample chunks: nchunk = ceil(Kp / (4096 / ppb))
 int reduce_planes_per_block(int Kp);
-// K4  weighted control reduction partials
-cudaError_t launch_weighted_controls(const DeviceState &d, cudaStream_t s);
+// K4  weighted control reduction partials; fuse_weights: K3 folded in (small K; then nb3 must equal nchunk)
+cudaError_t launch_weighted_controls(const DeviceState &d, bool fuse_weights, cudaStream_t s);
 // K5  fixed-order final sums -> record;  K6 merge of G records -> u_new, nominal, stats, counter++
 cudaError_t launch_finalize(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge(const DeviceState &d, cudaStream_t s);
