@@ -73,6 +73,24 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
 
+    def sample_once(self):
+        """One sample from the calling thread (used while the GPU is busy with the enqueued steps)."""
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # noqa: BLE001
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                              (0x4, "sw_power_cap"), (0x80, "hw_power_brake")):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
     def run(self):
         if not self.ok:
             return
@@ -307,6 +325,8 @@ def main():
     for _ in range(args.steps):
         ctl.enqueue()
     e1.record(stream)
+    if sampler:
+        sampler.sample_once()  # the steps are queued and running: at least one sample under load
     sync_all()
     ms_total = e0.elapsed_time(e1)
     launches = ctl.launch_count() * args.steps

@@ -530,3 +530,40 @@ def test_randomised_sweep_bit_exact_costs():
         # cost error <= 1e-5*c perturbs a weight by <= 1e-5*c/lambda: scale the control tolerance with it
         tol = max(U_TOL, 4e-5 * float(np.abs(o["cost"]).max()) / case["sp"]["lambda_"])
         assert err <= tol, (trial, model, K, T, err, tol, ess)
+
+
+@pytest.mark.parametrize("model,K,T", [("steering", 301, 600), ("diff_drive", 64, 2048), ("full_body", 40, 1500)])
+def test_long_horizons_use_opt_in_shared_memory(model, K, T):
+    """Horizons whose window / warm start / ring exceed the 48 KB default dynamic shared memory (both scan kernels)."""
+    case = make_case(model, K, T, seed=T)
+    pth = paths.sin_path(course_length=60.0, A1=1.0, omega1=0.1, delta1=0.0, delta2=0.0, delta3=0.0)
+    costs = {}
+    for mode in (_capi.SCAN_PRUNED, _capi.SCAN_LITERAL):
+        with _make_ctl(case) as ctl:
+            ctl.set_path(pth)
+            ctl.set_noise(case["eps"][None])
+            ctl.set_scan_mode(mode)
+            ctl.optimal_solution[0] = case["u0"]
+            ctl.solve(case["state"], 0.05)
+            costs[mode] = ctl.costs()
+            window, _ = ctl.window()
+    assert np.array_equal(costs[_capi.SCAN_PRUNED].view(np.uint32), costs[_capi.SCAN_LITERAL].view(np.uint32))
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], 0.05, window, case["eps"], case["u0"])
+    assert np.array_equal(costs[_capi.SCAN_PRUNED].view(np.uint32), tw["cost"].view(np.uint32))
+
+
+def test_many_handles_create_destroy():
+    """No leak / stale state across many short-lived handles (each owns streams, events, pinned and device memory)."""
+    import torch
+    case = make_case("diff_drive", 256, 15)
+    free0 = torch.cuda.mem_get_info()[0]
+    ref = None
+    for k in range(40):
+        with _make_ctl(case) as ctl:
+            ctl.set_seed(42, 0)
+            ctl.use_graph(k % 2 == 0)
+            u = ctl.solve(case["state"], case["dt"]).copy()
+            u = ctl.solve(case["state"], case["dt"]).copy()
+        ref = u if ref is None else ref
+        assert np.array_equal(u, ref)
+    assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20
