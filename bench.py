@@ -258,6 +258,8 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan", default="auto", choices=["auto", "literal", "pruned"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="sample-sharded solves: records exchanged by NVLink peer stores inside the finalize kernel, or by ncclAllGather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -294,12 +296,40 @@ def main():
         if shard_robots:
             ctl.set_shard(0, K, rank * R)
         else:
-            idt = torch.zeros(_capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
-            dist.broadcast(idt, 0)
             ctl.set_shard(rank * K, world * K, 0)
-            ctl.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+            exchange = args.exchange
+            if exchange == "p2p":
+                def all_ok(ok):
+                    f = torch.tensor([1 if ok else 0], device="cuda")
+                    dist.all_reduce(f, op=dist.ReduceOp.MIN)
+                    return int(f.item()) == 1
+                mine, err = None, None
+                try:
+                    mine = ctl.comm_export(world)
+                except _capi.MppiError as e:
+                    err = e
+                if all_ok(mine is not None):
+                    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+                    allh = [torch.zeros_like(t) for _ in range(world)]
+                    dist.all_gather(allh, t)
+                    try:
+                        ctl.comm_connect(b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh), rank, world)
+                        connected = True
+                    except _capi.MppiError as e:
+                        connected, err = False, e
+                    if not all_ok(connected):
+                        raise SystemExit(f"peer exchange connected on some ranks only ({err})")
+                else:  # CUDA IPC not available here: every rank falls back to NCCL
+                    if rank == 0:
+                        print(f"[bench] peer exchange unavailable ({err}); using NCCL", file=sys.stderr)
+                    exchange = "nccl"
+            if exchange == "nccl":
+                idt = torch.zeros(_capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(idt, 0)
+                ctl.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+            args.exchange = exchange
     # a non-default torch stream: the handle launches on it, so torch.cuda.Event timing sees the kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -312,14 +342,20 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-resident throughput: inputs uploaded once, K solves enqueued back to back -------------------
+    # NVML polling takes a driver lock and nvmlInit is slow: rank 0 only, and set up BEFORE the barrier so that the
+    # other ranks' timed regions do not contain rank 0's NVML start-up
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("MPPI_BENCH_NO_CLOCKS")) else None
+    if sampler:
+        sampler.sample_once()
+        sampler.samples.clear()
     ctl.upload(states, 0.1, with_nominal=True)
     for _ in range(args.warmup):
         ctl.enqueue()
-    sync_all()
-    # NVML polling takes a driver lock: rank 0 only, so that 8 ranks do not slow each other's launches
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    sync_all()
+    if sampler:
+        sampler.samples.clear()  # keep only what is sampled inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -329,6 +365,8 @@ def main():
         sampler.sample_once()  # the steps are queued and running: at least one sample under load
     sync_all()
     ms_total = e0.elapsed_time(e1)
+    if os.environ.get("MPPI_BENCH_DEBUG"):
+        print(f"[bench] rank {rank}: {ms_total / args.steps:.4f} ms/step device-resident", file=sys.stderr, flush=True)
     launches = ctl.launch_count() * args.steps
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -362,6 +400,7 @@ def main():
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = peaks()
+        clocks = clocks or {"sm_mhz": None, "sm_max_mhz": sm_max_mhz, "reasons": ["sampling disabled"]}
         clk = clocks.get("sm_mhz") or sm_max_mhz
         fp32_peak_max = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
         fp32_peak_obs = 148 * 128 * 2 * clk * 1e6 / 1e12
@@ -393,7 +432,9 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": args.workload, "model": model, "K_per_gpu": K, "K_global": K * (1 if shard_robots else world),
                           "T": T, "U": U, "robots_per_gpu": R, "sharding": "robots" if shard_robots else "samples",
-                          "collective": "none" if (shard_robots or world == 1) else "one ncclAllGather of (c_min, sum w, sum w^2, sum w*u) per solve",
+                          "collective": "none" if (shard_robots or world == 1) else (
+                              "records (c_min, sum w, sum w^2, sum w*u) stored into every peer's buffer over NVLink by the finalize kernel, merge waits on flags"
+                              if args.exchange == "p2p" else "one ncclAllGather of (c_min, sum w, sum w^2, sum w*u) per solve"),
                           "l2": f"noise tensor {4 * U * local_steps / 1e6:.0f} MB per solve vs 126 MB L2 (inputs larger than L2, no flush)",
                           "scan": args.scan, "ess": stats["ess"]},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

@@ -15,6 +15,7 @@ DEBUG_NONE, DEBUG_NEAREST, DEBUG_STATES = 0, 1, 2
 SCAN_AUTO, SCAN_LITERAL, SCAN_PRUNED = 0, 1, 2
 WINDOW_AUTO, WINDOW_HOST, WINDOW_DEVICE = 0, 1, 2
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class MppiParams(C.Structure):
@@ -65,6 +66,8 @@ SYMBOLS = {
     "mppi_last_launch_count": (C.c_int, [C.c_void_p]),
     "mppi_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "mppi_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mppi_comm_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mppi_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mppi_merge_partials": (C.c_int, [_P(C.c_float), C.c_int, C.c_int, C.c_double, _P(C.c_float), _P(C.c_double)]),
     "mppi_calc_ref_path": (C.c_int, [_P(C.c_double), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_int, _P(C.c_double), _P(C.c_int)]),

@@ -126,6 +126,17 @@ class _MPPIBase:
         buf = C.create_string_buffer(unique_id, _capi.COMM_ID_BYTES)
         self._check(self.lib.mppi_comm_init(self._h, buf, rank, n_ranks))
 
+    def comm_export(self, n_ranks) -> bytes:
+        """NVLink peer exchange, step 1: this rank's exchange-buffer IPC handle (all-gather these across ranks)."""
+        buf = C.create_string_buffer(_capi.IPC_HANDLE_BYTES)
+        self._check(self.lib.mppi_comm_export(self._h, int(n_ranks), buf))
+        return buf.raw
+
+    def comm_connect(self, handles: bytes, rank, n_ranks):
+        """NVLink peer exchange, step 2: map every peer's buffer (handles = all ranks' handles concatenated)."""
+        buf = C.create_string_buffer(handles, _capi.IPC_HANDLE_BYTES * n_ranks)
+        self._check(self.lib.mppi_comm_connect(self._h, buf, rank, n_ranks))
+
     # -- the cycle --------------------------------------------------------------------------------------
     def solve(self, state=None, dt=None):
         """sampling(); predict_States(); calc_Weights(); determine_OptimalSolution();  (DD:352-358)

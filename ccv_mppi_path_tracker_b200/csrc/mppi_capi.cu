@@ -109,6 +109,12 @@ struct mppi_handle_s {
   // collective
   void *comm = nullptr;
   int rank = 0, n_ranks = 1;
+  // NVLink peer exchange (instead of NCCL): own buffer, peers' IPC mappings
+  bool p2p = false;
+  int xchg_ranks = 0;
+  void *xchg_buf = nullptr;
+  std::vector<void *> xchg_peer_ptrs;
+  void **d_xchg_peers = nullptr;
   std::string err;
 };
 
@@ -225,6 +231,14 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
   }
   CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
   ++n;
+  if (h->p2p) {
+    CU_TRY(h, launch_finalize_push(d, s));
+    ++n;
+    CU_TRY(h, launch_merge_wait(d, s));
+    ++n;
+    h->launch_count = n;
+    return MPPI_OK;
+  }
   if (fused_tail(h)) {
     CU_TRY(h, launch_finalize_merge(d, s));
     ++n;
@@ -319,9 +333,14 @@ int capture(mppi_handle h, bool with_copies, cudaGraphExec_t *out) {
   return MPPI_OK;
 }
 
-void copy_out(mppi_handle h, double *u_nominal) {
+int copy_out(mppi_handle h, double *u_nominal) {
   const size_t n = (size_t)h->R * h->d.planes;
   for (size_t k = 0; k < n; ++k) u_nominal[k] = (double)h->h_out[k];
+  if (h->p2p)
+    for (int r = 0; r < h->R; ++r)
+      if (h->h_out[n + (size_t)r * 4 + 3] != 0.f)
+        return fail(h, MPPI_ERR_NCCL, "peer exchange timed out: a rank's record did not arrive (are all ranks solving?)");
+  return MPPI_OK;
 }
 
 }  // namespace
@@ -463,6 +482,9 @@ int mppi_destroy(mppi_handle h) {
   if (h->side_stream) cudaStreamSynchronize(h->side_stream);
   invalidate_graphs(h);
   if (h->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(h->comm);
+  for (size_t g = 0; g < h->xchg_peer_ptrs.size(); ++g)
+    if (h->xchg_peer_ptrs[g] && h->xchg_peer_ptrs[g] != h->xchg_buf) cudaIpcCloseMemHandle(h->xchg_peer_ptrs[g]);
+  cudaFree(h->xchg_buf); cudaFree(h->d_xchg_peers); cudaFree(h->d.xchg_seq); cudaFree(h->d.xchg_ticket);
   DeviceState &d = h->d;
   if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
@@ -639,8 +661,7 @@ int mppi_download(mppi_handle h, double *u_nominal) {
   CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->staged_pending = false;
-  copy_out(h, u_nominal);
-  return MPPI_OK;
+  return copy_out(h, u_nominal);
 }
 
 int mppi_synchronize(mppi_handle h) {
@@ -665,8 +686,7 @@ int mppi_solve(mppi_handle h, const double *state, double dt, double *u_nominal)
     CU_TRY(h, cudaGraphLaunch(h->exec_solve, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_inputs = h->have_nominal = true;
-    copy_out(h, u_nominal);
-    return MPPI_OK;
+    return copy_out(h, u_nominal);
   }
   int rc = mppi_upload(h, state, dt, u_nominal);
   if (rc) return rc;
@@ -832,9 +852,13 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     launch_weighted_controls(d, fused_weights(h), s);
     cudaEventRecord(ev[4], s);
     const bool fused = fused_tail(h);
-    if (fused) launch_finalize_merge(d, s); else launch_finalize(d, s);
+    if (h->p2p) launch_finalize_push(d, s);
+    else if (fused) launch_finalize_merge(d, s);
+    else launch_finalize(d, s);
     cudaEventRecord(ev[5], s);
-    if (!fused) {
+    if (h->p2p) {
+      launch_merge_wait(d, s);
+    } else if (!fused) {
       if (h->n_ranks > 1 &&
           g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
         rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
@@ -889,6 +913,56 @@ int mppi_comm_init(mppi_handle h, const void *id, int rank, int n_ranks) {
   h->d.n_ranks = n_ranks;
   h->n_ranks = n_ranks;
   h->rank = rank;
+  invalidate_graphs(h);
+  return MPPI_OK;
+}
+
+int mppi_comm_export(mppi_handle h, int n_ranks, void *handle_out) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!handle_out || n_ranks < 2 || n_ranks > 32) return fail(h, MPPI_ERR_INVALID, "need 2 <= n_ranks <= 32 and a handle buffer");
+  if (h->comm || h->xchg_buf) return fail(h, MPPI_ERR_STATE, "communicator already initialised");
+  CU_TRY(h, cudaSetDevice(h->device));
+  const DeviceState &d = h->d;
+  const size_t bytes = kExchangeHeaderBytes + sizeof(float) * 2 * (size_t)n_ranks * d.R * d.rec_stride;
+  CU_TRY(h, cudaMalloc(&h->xchg_buf, bytes));
+  CU_TRY(h, cudaMemset(h->xchg_buf, 0, bytes));
+  CU_TRY(h, cudaMalloc((void **)&h->d.xchg_seq, sizeof(unsigned int)));
+  CU_TRY(h, cudaMemset(h->d.xchg_seq, 0, sizeof(unsigned int)));
+  CU_TRY(h, cudaMalloc((void **)&h->d.xchg_ticket, 2 * sizeof(unsigned int)));
+  CU_TRY(h, cudaMemset(h->d.xchg_ticket, 0, 2 * sizeof(unsigned int)));
+  CU_TRY(h, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ipc;
+  CU_TRY(h, cudaIpcGetMemHandle(&ipc, h->xchg_buf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &ipc, sizeof ipc);
+  h->xchg_ranks = n_ranks;
+  return MPPI_OK;
+}
+
+int mppi_comm_connect(mppi_handle h, const void *handles, int rank, int n_ranks) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!handles || !h->xchg_buf || n_ranks != h->xchg_ranks || rank < 0 || rank >= n_ranks)
+    return fail(h, MPPI_ERR_INVALID, "mppi_comm_connect needs the handles of all ranks of the preceding mppi_comm_export");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->xchg_peer_ptrs.assign(n_ranks, nullptr);
+  for (int g = 0; g < n_ranks; ++g) {
+    if (g == rank) {
+      h->xchg_peer_ptrs[g] = h->xchg_buf;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, (const char *)handles + (size_t)g * MPPI_IPC_HANDLE_BYTES, sizeof ipc);
+    CU_TRY(h, cudaIpcOpenMemHandle(&h->xchg_peer_ptrs[g], ipc, cudaIpcMemLazyEnablePeerAccess));
+  }
+  CU_TRY(h, cudaMalloc((void **)&h->d_xchg_peers, sizeof(void *) * n_ranks));
+  CU_TRY(h, cudaMemcpy(h->d_xchg_peers, h->xchg_peer_ptrs.data(), sizeof(void *) * n_ranks, cudaMemcpyHostToDevice));
+  h->d.xchg_buf = h->xchg_buf;
+  h->d.xchg_peers = h->d_xchg_peers;
+  h->d.xchg_rank = rank;
+  h->d.n_ranks = n_ranks;
+  h->n_ranks = n_ranks;
+  h->rank = rank;
+  h->p2p = true;
   invalidate_graphs(h);
   return MPPI_OK;
 }

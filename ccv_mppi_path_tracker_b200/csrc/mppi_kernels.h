@@ -67,6 +67,11 @@ struct DeviceState {
   const double *state64 = nullptr;   // [R][2] pose x, y (in inbuf)
   const unsigned char *win_fixed = nullptr;  // [R] 1 = window given by mppi_set_window (host-built), skip
   int *cur_index = nullptr;          // [R] current_index_ of the last solve
+  // NVLink record exchange (C1 without NCCL): this rank's buffer, the peers' buffers (IPC-mapped), sequence
+  void *xchg_buf = nullptr;
+  void *const *xchg_peers = nullptr;  // [G] device array of exchange-buffer base pointers (own one included)
+  unsigned int *xchg_seq = nullptr, *xchg_ticket = nullptr;  // solve sequence; two "last block" tickets
+  int xchg_rank = 0;
   GridHeader *grid_hdr = nullptr;
   uint32_t *grid_cells = nullptr;
   int grid_max_cells = 0;
@@ -74,6 +79,7 @@ struct DeviceState {
 };
 
 constexpr int kHeaderBytes = 256;
+constexpr int kExchangeHeaderBytes = 256;  // flags[2][G] (G <= 32) at the start of an exchange buffer
 constexpr int kWeightBlock = 256;   // threads of the weight kernel, 4 samples per thread
 constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
 constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
@@ -102,6 +108,10 @@ cudaError_t launch_weighted_controls(const DeviceState &d, bool fuse_weights, cu
 // K5  fixed-order final sums -> record;  K6 merge of G records -> u_new, nominal, stats, counter++
 cudaError_t launch_finalize(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge(const DeviceState &d, cudaStream_t s);
+// C1 over NVLink peer memory instead of NCCL: K5 whose last block pushes the record into every peer's exchange
+// buffer, and K6 that waits for the peers' flags (one process per GPU, buffers shared through CUDA IPC)
+cudaError_t launch_finalize_push(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_merge_wait(const DeviceState &d, cudaStream_t s);
 // K5 + K6 in one launch when the handle is not sharded (identical results)
 cudaError_t launch_finalize_merge(const DeviceState &d, cudaStream_t s);
 

@@ -179,6 +179,14 @@ int mppi_last_launch_count(mppi_handle h);
 /* rank 0 creates the id, the host launcher broadcasts it (torch.distributed / MPI / a file) */
 int mppi_comm_get_unique_id(void *id_out /* MPPI_COMM_ID_BYTES */);
 int mppi_comm_init(mppi_handle h, const void *id, int rank, int n_ranks);
+/* The same exchange without NCCL, over NVLink peer memory: every rank exports an exchange buffer (CUDA IPC handle,
+ * MPPI_IPC_HANDLE_BYTES), the launcher all-gathers the handles, every rank connects.  Afterwards the finalize
+ * kernel of a solve stores this rank's record straight into every peer's buffer and raises a flag there; the merge
+ * kernel waits for the flags.  One process per GPU; every rank must call mppi_solve / mppi_enqueue the same number
+ * of times (a missing peer makes the solve return MPPI_ERR_NCCL after a ~2 s device-side timeout). */
+#define MPPI_IPC_HANDLE_BYTES 64
+int mppi_comm_export(mppi_handle h, int n_ranks, void *handle_out /* MPPI_IPC_HANDLE_BYTES */);
+int mppi_comm_connect(mppi_handle h, const void *handles /* n_ranks x MPPI_IPC_HANDLE_BYTES */, int rank, int n_ranks);
 /* This rank's partial record of the last solve for one robot: {c_min, sum w, sum w^2, 0, N[(T-1)*U]} with
  * w = exp(-(c - c_min)/lambda) over the local samples and N the weighted sum of the clamped samples -- what the
  * collective exchanges.  Lets a host that owns its own transport (MPI, shared memory) do the exchange itself. */
