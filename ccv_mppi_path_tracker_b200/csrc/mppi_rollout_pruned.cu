@@ -14,7 +14,9 @@
 //     with c the cell centre, r its half diagonal (inflated) and D_j = |c - r_j|:  for p in the cell
 //     | |p - r_j| - D_j | <= r, so a point with D_j > min_k D_k + 2r is strictly farther from p than the point
 //     that attains the minimum at c.  Candidates = { j : D_j <= D_min + 2r } (+ 1e-4 relative slack, four orders
-//     of magnitude above the FP32 rounding of the distances involved).
+//     of magnitude above the FP32 rounding of the distances involved), thinned by a corner test against the point
+//     k0 nearest to c: |p - r_j|^2 - |p - r_k0|^2 is affine in p, positive at the four cell corners => r_j is
+//     strictly farther than r_k0 everywhere in the cell (this keeps far-from-path cells at 3-5 candidates).
 // K2 looks the cell of each predicted state up (one FMA + float->int per axis, one 32-bit load) and evaluates
 // exact squared distances only for that range -- about 4-12 points instead of T, independent of T -- with
 // Blackwell's packed FP32 pipe (sub/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2, two window points per instruction,
@@ -203,14 +205,40 @@ __global__ void __launch_bounds__(128)
   const float ccx = gh.x0 + ((float)ix + 0.5f) * gh.h, ccy = gh.y0 + ((float)iy + 0.5f) * gh.h;
   const float r = 0.70710678f * gh.h * kCellInflate + 1.0e-6f * (fabsf(ccx) + fabsf(ccy));
   float m = INFINITY;
-  for (int j = 0; j < T; ++j) m = fminf(m, dist2(ccx, ccy, s_win[j].x, s_win[j].y));
+  int k0 = 0;
+  for (int j = 0; j < T; ++j) {
+    const float dj = dist2(ccx, ccy, s_win[j].x, s_win[j].y);
+    if (dj < m) {
+      m = dj;
+      k0 = j;
+    }
+  }
   const float reach = sqrtf(m) + 2.f * r;
   const float thr = reach * reach * kCandSlack;
+  // Second, sharper filter for the survivors of the circle test: |p - r_j|^2 - |p - r_k0|^2 is affine in p, so if
+  // it is positive at the four corners of the (inflated) cell it is positive everywhere in it -- r_j is then
+  // strictly farther than r_k0 from every position in the cell and can never be the nearest point.  The margin
+  // (1e-5 of the largest squared distance involved) is an order above the FP32 rounding of K2's own distances.
+  const float hs = 0.5f * gh.h * kCellInflate + 1.0e-6f * (fabsf(ccx) + fabsf(ccy));
+  const float kx = s_win[k0].x, ky = s_win[k0].y;
+  float dk[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dk[c] = dist2(ccx + ((c & 1) ? hs : -hs), ccy + ((c & 2) ? hs : -hs), kx, ky);
   int lo = T, hi = -1;
   for (int j = 0; j < T; ++j) {
-    if (dist2(ccx, ccy, s_win[j].x, s_win[j].y) <= thr) {
-      lo = min(lo, j);
-      hi = j;
+    const float jx = s_win[j].x, jy = s_win[j].y;
+    if (dist2(ccx, ccy, jx, jy) <= thr) {
+      float gap = INFINITY, scale = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float dj = dist2(ccx + ((c & 1) ? hs : -hs), ccy + ((c & 2) ? hs : -hs), jx, jy);
+        gap = fminf(gap, dj - dk[c]);
+        scale = fmaxf(scale, dj + dk[c]);
+      }
+      if (!(gap > 1.0e-5f * scale + 1.0e-30f)) {  // not provably farther than r_k0 everywhere (or NaN): candidate
+        lo = min(lo, j);
+        hi = j;
+      }
     }
   }
   // pairs of points, two pairs per scan iteration; an empty candidate set can only arise from NaNs: scan everything
