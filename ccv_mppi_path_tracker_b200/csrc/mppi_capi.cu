@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -396,7 +397,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.n_ranks = 1;
   // candidate grid of the pruned scan: building it costs ~cells*T distance evaluations per robot and solve, the
   // rollouts K*T*(~100 instr): keep the grid below a few per cent of that
-  d.grid_max_cells = num_samples / 2 < 256 ? 256 : (num_samples / 2 > 16384 ? 16384 : num_samples / 2);
+  d.grid_max_cells = num_samples / 2 < 256 ? 256 : (num_samples / 2 > 65536 ? 65536 : num_samples / 2);
+  if (const char *e = getenv("MPPI_GRID_MAX_CELLS")) d.grid_max_cells = atoi(e);  // tuning experiments only
+  if (const char *e = getenv("MPPI_GRID_H_MIN")) d.grid_h_min = (float)atof(e);
   if (d.planes > 65535) {
     delete h;
     return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");
