@@ -92,28 +92,24 @@ __device__ __forceinline__ float scan_pairs(unsigned pairs_s, int q0, int n2, fl
 }
 
 struct GridView {
-  const uint32_t *cells;  // [ny][nx]: first pair | (number of 2-pair iterations) << 16
-  float inv_h, cx, cy;    // cell index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy))
-  unsigned nx, ny;
-  int all_n2;             // iterations that cover the whole (padded) window
+  const uint32_t *cells;  // [ny + 2][nx + 2]: first pair | (number of 2-pair iterations) << 16; the one-cell
+                          // border ring says "scan the whole window" (positions outside the grid are clamped to it)
+  float inv_h, cx, cy;    // table index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy)) (border included)
+  int nx2, ny2;           // nx + 2, ny + 2
 };
 
-// Exact min_j min(d2(p, r_j), 1e4) over the whole window.
+// Exact min_j min(d2(p, r_j), 1e4) over the whole window.  Branch-free lookup: the float->int conversion
+// saturates, the clamp sends everything outside the grid to the border ring.
 __device__ __forceinline__ float min_dist2_grid(const GridView &g, unsigned pairs_s, float x, float y) {
-  const unsigned ix = (unsigned)__float2int_rd(fmaf(x, g.inv_h, g.cx));
-  const unsigned iy = (unsigned)__float2int_rd(fmaf(y, g.inv_h, g.cy));
-  int q0 = 0, n2 = g.all_n2;
-  if (ix < g.nx && iy < g.ny) {
-    const uint32_t e = __ldg(g.cells + (iy * g.nx + ix));
-    q0 = (int)(e & 0xFFFFu);
-    n2 = (int)(e >> 16);
-  }
-  return scan_pairs(pairs_s, q0, n2, x, y, kDist2Cap);
+  const int ix = min(max(__float2int_rd(fmaf(x, g.inv_h, g.cx)), 0), g.nx2 - 1);
+  const int iy = min(max(__float2int_rd(fmaf(y, g.inv_h, g.cy)), 0), g.ny2 - 1);
+  const uint32_t e = __ldg(g.cells + (iy * g.nx2 + ix));
+  return scan_pairs(pairs_s, (int)(e & 0xFFFFu), (int)(e >> 16), x, y, kDist2Cap);
 }
 
 // 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, so the normals of future control
 // steps stream in behind the arithmetic without ever blocking a register scoreboard
-__device__ __forceinline__ void cp_async_f32(unsigned smem_dst, const float *gsrc) {
+__device__ __forceinline__ void cp_async_f32(unsigned smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -178,18 +174,18 @@ __global__ void __launch_bounds__(128)
         for (int it = 0; it < 64; ++it) {
           nx = (int)ceilf(w / h);
           ny = (int)ceilf(hgt / h);
-          if ((long long)nx * ny <= max_cells && nx < 32768 && ny < 32768) break;
+          if ((long long)(nx + 2) * (ny + 2) <= max_cells && nx < 32768 && ny < 32768) break;
           h *= 1.05f;
         }
-        if ((long long)nx * ny <= max_cells) {
+        if ((long long)(nx + 2) * (ny + 2) <= max_cells) {
           gh.nx = nx;
           gh.ny = ny;
           gh.h = h;
           gh.inv_h = 1.0f / h;
           gh.x0 = xmin - margin;
           gh.y0 = ymin - margin;
-          gh.cx = -gh.x0 * gh.inv_h;
-          gh.cy = -gh.y0 * gh.inv_h;
+          gh.cx = 1.0f - gh.x0 * gh.inv_h;  // + 1: the border ring occupies table column / row 0
+          gh.cy = 1.0f - gh.y0 * gh.inv_h;
         }
       }
       s_h = gh;
@@ -198,10 +194,15 @@ __global__ void __launch_bounds__(128)
   }
   __syncthreads();
   const GridHeader gh = s_h;
-  const int n_cells = gh.nx * gh.ny;
+  const int nx2 = gh.nx + 2, ny2 = gh.ny + 2;  // a failed geometry (nx = ny = 0) leaves a 2 x 2 table of border cells
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= n_cells) return;
-  const int ix = cell % gh.nx, iy = cell / gh.nx;
+  if (cell >= nx2 * ny2) return;
+  const int tx = cell % nx2, ty = cell / nx2;
+  if (tx == 0 || ty == 0 || tx == nx2 - 1 || ty == ny2 - 1) {  // border ring: the whole (padded) window
+    cells[(size_t)robot * max_cells + cell] = (uint32_t)(((T + 1) / 2 + 1) / 2) << 16;
+    return;
+  }
+  const int ix = tx - 1, iy = ty - 1;
   const float ccx = gh.x0 + ((float)ix + 0.5f) * gh.h, ccy = gh.y0 + ((float)iy + 0.5f) * gh.h;
   const float r = 0.70710678f * gh.h * kCellInflate + 1.0e-6f * (fabsf(ccx) + fabsf(ccy));
   float m = INFINITY;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
   if (i < K) {
     const uint32_t *cp = cells + (size_t)robot * max_cells;
     asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
-    const GridView gv{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, (unsigned)s_gh.nx, (unsigned)s_gh.ny, (NP + 1) / 2};
+    const GridView gv{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.ny + 2};
     unsigned pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
     unsigned ring_s = (unsigned)__cvta_generic_to_shared(s_eps + threadIdx.x);
     unsigned nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
