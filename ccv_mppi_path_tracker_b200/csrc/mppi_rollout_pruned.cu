@@ -98,12 +98,15 @@ struct GridView {
   int nx2, ny2;           // nx + 2, ny + 2
 };
 
-// Exact min_j min(d2(p, r_j), 1e4) over the whole window.  Branch-free lookup: the float->int conversion
-// saturates, the clamp sends everything outside the grid to the border ring.
-__device__ __forceinline__ float min_dist2_grid(const GridView &g, unsigned pairs_s, float x, float y) {
+// Candidate range of the cell that contains (x, y).  Branch-free lookup: the float->int conversion saturates, the
+// clamp sends everything outside the grid to the border ring.
+__device__ __forceinline__ uint32_t grid_cell(const GridView &g, float x, float y) {
   const int ix = min(max(__float2int_rd(fmaf(x, g.inv_h, g.cx)), 0), g.nx2 - 1);
   const int iy = min(max(__float2int_rd(fmaf(y, g.inv_h, g.cy)), 0), g.ny2 - 1);
-  const uint32_t e = __ldg(g.cells + (iy * g.nx2 + ix));
+  return __ldg(g.cells + (iy * g.nx2 + ix));
+}
+// Exact min_j min(d2(p, r_j), 1e4) over the whole window, given the cell entry of (x, y).
+__device__ __forceinline__ float min_dist2_cell(uint32_t e, unsigned pairs_s, float x, float y) {
   return scan_pairs(pairs_s, (int)(e & 0xFFFFu), (int)(e >> 16), x, y, kDist2Cap);
 }
 
@@ -357,24 +360,30 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
         dst[u] = sample_control(lds32_volatile(src + u * 512u), sigma, lds32(nom + u * 4u), lo[u], hi[u]);
       if (steer_off) dst[2] = 0.f;  // FB:517
     };
-    // one iteration: cost terms of state t, then the Euler step with the controls `cur` (next step's in `nxt`)
+    // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
+    // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
+    // current state, loaded one iteration earlier).
+    uint32_t cell = grid_cell(gv, x, y);
     auto advance = [&](const float *cur, const float *nxt) {
-      acc.path += min_dist2_grid(gv, pairs_s, x, y);
-      const float dv = cur[0] - v_ref;
-      acc.vel = fmaf(dv, dv, acc.vel);
-      if (MODEL == kFullBody) {
-        float zx, zy;
-        zmp_model(sP, cur[0], nxt[0], cur[1], cur[2], cur[3], nxt[3], cur[4], nxt[4], roll, pitch, zx, zy);
-        acc.zmp = fmaf(zy, zy, acc.zmp);
-        const float dr = nxt[3] - cur[3];
-        acc.droll = fmaf(dr, dr, acc.droll);
-        if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
-      }
+      const float x0 = x, y0 = y, roll0 = roll, pitch0 = pitch;
       const float heading = MODEL == kDiffDrive ? yaw : yaw + cur[2];
       step_pose(x, y, yaw, cur[0], cur[1], heading, dt);
       if (MODEL == kFullBody) {
         roll = fmaf(cur[3], dt, roll);
         pitch = fmaf(cur[4], dt, pitch);
+      }
+      const uint32_t cell_next = grid_cell(gv, x, y);
+      acc.path += min_dist2_cell(cell, pairs_s, x0, y0);
+      cell = cell_next;
+      const float dv = cur[0] - v_ref;
+      acc.vel = fmaf(dv, dv, acc.vel);
+      if (MODEL == kFullBody) {
+        float zx, zy;
+        zmp_model(sP, cur[0], nxt[0], cur[1], cur[2], cur[3], nxt[3], cur[4], nxt[4], roll0, pitch0, zx, zy);
+        acc.zmp = fmaf(zy, zy, acc.zmp);
+        const float dr = nxt[3] - cur[3];
+        acc.droll = fmaf(dr, dr, acc.droll);
+        if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
       }
     };
 #pragma unroll
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
       for (int u = 0; u < U; ++u) ca[u] = cb[u];
       make(t + 2, (unsigned)((t + 2) & 3), cb);
     }
-    if (MODEL != kFullBody) acc.path += min_dist2_grid(gv, pairs_s, x, y);  // state T-1: path term only (D1)
+    if (MODEL != kFullBody) acc.path += min_dist2_cell(cell, pairs_s, x, y);  // state T-1: path term only (D1)
     float yaw0_err = 0.f;
     if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
       const float4 w01 = s_pairs[0];
