@@ -410,7 +410,7 @@ def main():
         achieved = local_steps * fl / t_k2 / 1e12
         # DRAM traffic of one K2 launch from the committed ncu --set full capture of this workload
         # (profiles/r01_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
-        traffic = 838.5e6 if args.workload == "diff_drive_K1M_T100" else None
+        traffic = 838.2e6 if args.workload == "diff_drive_K1M_T100" else None
         roofline = {"bound": "fp32", "kernel": "rollout_cost", "achieved": achieved, "peak": fp32_peak_max,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": traffic,
                     "traffic_note": "bytes per launch (ncu); algorithmic bytes = 4*U per rollout-step = 830.5e6",
