@@ -464,6 +464,8 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
+  CU_NEW(make_eps_tensor_map(d));
+  if (const char *e = getenv("MPPI_K2_RING")) d.k2_ring = atoi(e);  // tuning experiments only
   CU_NEW(cudaMalloc((void **)&d.grid_hdr, sizeof(GridHeader) * (size_t)d.R));
   CU_NEW(cudaMemset(d.grid_hdr, 0, sizeof(GridHeader) * (size_t)d.R));
   CU_NEW(cudaMalloc((void **)&d.grid_cells, sizeof(uint32_t) * (size_t)d.R * d.grid_max_cells));

@@ -1,5 +1,6 @@
 // mppi_kernels.h -- device-side data layout and kernel launchers of the MPPI core (internal, not the ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -76,6 +77,10 @@ struct DeviceState {
   uint32_t *grid_cells = nullptr;
   int grid_max_cells = 0;
   float grid_h_min = 0.08f, grid_margin = 3.0f;  // measured optimum at K = 2^20 (0.04 .. 0.125 tried)
+  // K2 noise ring: 1 = per-warp TMA tiles of the noise tensor (needs eps_map), 0 = per-thread cp.async
+  int k2_ring = 1;
+  bool eps_map_valid = false;
+  CUtensorMap eps_map;  // 2-D {Kp, R * planes} f32, box {32, 4 * U}
 };
 
 constexpr int kHeaderBytes = 256;
@@ -99,6 +104,8 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s);
 // K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
 cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s);
 bool pruned_scan_supported(int T, int planes);
+// tensor map of d.eps for K2's TMA ring (after d.eps, Kp, R, planes, U are final)
+cudaError_t make_eps_tensor_map(DeviceState &d);
 // K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 // planes per block of K4 (1, 2 or 4) and the matching number of sample chunks: nchunk = ceil(Kp / (4096 / ppb))

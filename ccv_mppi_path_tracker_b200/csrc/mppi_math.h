@@ -75,19 +75,56 @@ MPPI_HD uint32_t float_to_bits(float f) {
 #endif
 }
 
-// clamp: DD:62-67 (NaN falls through both tests, as in the reference)
-MPPI_HD float clamp_ref(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// clamp: DD:62-67, `if (v < lo) v = lo; else if (v > hi) v = hi;` -- NaN falls through both tests.
+// Evaluated as min.NaN(max.NaN(v, lo), hi): two FMNMX instead of two compare/select pairs, NaN still passes
+// through.  Identical to the reference's result for lo <= hi (mppi_create rejects lo > hi) except for the SIGN of a
+// zero result when v and the bound are zeros of opposite sign (PTX orders -0 < +0) -- no effect on any distance,
+// cost or control value.  The host version reproduces the PTX semantics bit for bit.
+MPPI_HD float max_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  if (a != a || b != b) return bits_to_float(0x7fffffffu);
+  if (a == b) return bits_to_float(float_to_bits(a) & float_to_bits(b));  // +0 wins over -0
+  return a > b ? a : b;
+#endif
+}
+MPPI_HD float min_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  if (a != a || b != b) return bits_to_float(0x7fffffffu);
+  if (a == b) return bits_to_float(float_to_bits(a) | float_to_bits(b));  // -0 wins over +0
+  return a < b ? a : b;
+#endif
+}
+MPPI_HD float clamp_ref(float v, float lo, float hi) { return min_nan(max_nan(v, lo), hi); }
 
 // sampling (D5): std::normal_distribution(mean, sigma) returns z*sigma + mean; then clamp (DD:96-99)
 MPPI_HD float sample_control(float eps, float sigma, float mean, float lo, float hi) {
   return clamp_ref(fmaf(eps, sigma, mean), lo, hi);
 }
 
+// sin and cos on [-pi/4, pi/4]: the classic single-precision minimax polynomials.
+MPPI_HD void sincos_poly(float r, float &sn, float &cs) {
+  float z = r * r;
+  float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, z, -1.6666654611e-1f);
+  sn = fmaf(sp, z * r, r);
+  float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, z, 4.166664568298827e-2f);
+  cs = fmaf(cp, z * z, fmaf(z, -0.5f, 1.0f));
+}
+
 // sin and cos of one angle, same bits on host and device.
-// Cody-Waite 3-term reduction by pi/2 (round-to-nearest via the 1.5*2^23 magic constant) and the classic
-// single-precision minimax polynomials on [-pi/4, pi/4]; |a| < 2^22*pi/2 keeps the quadrant exact, the
-// reduced argument is accurate to ~1 ulp for |a| < ~1e4 (yaw after a 10 s horizon is < 40 rad).
-MPPI_HD void sincos_f32(float a, float &s, float &c) {
+// Cody-Waite 3-term reduction by pi/2 (round-to-nearest via the 1.5*2^23 magic constant) and sincos_poly on the
+// reduced argument; |a| < 2^22*pi/2 keeps the quadrant exact, the reduced argument is accurate to ~1 ulp for
+// |a| < ~1e4 (yaw after a 10 s horizon is < 40 rad).
+MPPI_HD void sincos_reduce(float a, float &s, float &c) {
   const float kMagic = 12582912.0f;           // 1.5 * 2^23
   const float kTwoOverPi = 0.636619772367581f;
   const float kPio2Hi = 1.5707963705062866f;   // (float)(pi/2)
@@ -99,17 +136,70 @@ MPPI_HD void sincos_f32(float a, float &s, float &c) {
   float r = fmaf(k, -kPio2Hi, a);
   r = fmaf(k, -kPio2Mid, r);
   r = fmaf(k, -kPio2Lo, r);
-  float z = r * r;
-  float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
-  sp = fmaf(sp, z, -1.6666654611e-1f);
-  float sn = fmaf(sp, z * r, r);
-  float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
-  cp = fmaf(cp, z, 4.166664568298827e-2f);
-  float cs = fmaf(cp, z * z, fmaf(z, -0.5f, 1.0f));
+  float sn, cs;
+  sincos_poly(r, sn, cs);
   float so = (q & 1u) ? cs : sn;
   float co = (q & 1u) ? sn : cs;
   s = (q & 2u) ? -so : so;
   c = ((q + 1u) & 2u) ? -co : co;
+}
+// Same function, same bits: for |a| <= 0.78 (< pi/4) the reduction is the identity (k = 0, r = a, quadrant 0), so
+// the polynomial is evaluated directly -- the common case for steering / direction angles (|a| <= 30 deg).
+// SMALL = the caller has proved |a| <= kSmallAngle (bounded controls): same bits, no test.
+constexpr float kSmallAngle = 0.78f;
+template <bool SMALL = false>
+MPPI_HD void sincos_f32(float a, float &s, float &c) {
+  if (SMALL || fabsf(a) <= kSmallAngle) {
+    sincos_poly(a, s, c);
+  } else {
+    sincos_reduce(a, s, c);
+  }
+}
+
+// sin and cos of a per-step angle INCREMENT (w*dt, roll_v*dt, pitch_v*dt).  For |a| <= 0.35 rad a degree-5 / degree-6
+// minimax pair (|sin error| < 1.4e-8 relative, |cos error| < 1.1e-10, both below half an FP32 ulp); beyond that
+// sincos_f32.  Part of the FP32 contract (host twin and device take the same branch on the same bits).
+constexpr float kSmallIncrement = 0.35f;
+template <bool SMALL = false>
+MPPI_HD void sincos_increment(float a, float &s, float &c) {
+  if (SMALL || fabsf(a) <= kSmallIncrement) {
+    float z = a * a;
+    s = fmaf(fmaf(z, 8.316085115305715e-3f, -1.6666633325849287e-1f), z * a, a);
+    c = fmaf(fmaf(fmaf(z, -1.3864750323901004e-3f, 4.166661078295986e-2f), z, -0.5f), z, 1.0f);
+  } else {
+    sincos_f32(a, s, c);
+  }
+}
+
+// (c, s) <- (c, s) rotated by the angle whose cosine / sine are (cd, sd): the heading recurrence.
+// predict_NextState (DD:106-108) evaluates cos(yaw), sin(yaw) with yaw_{t+1} = yaw_t + w_t*dt; the contract carries
+// (cos yaw, sin yaw) through the horizon instead of re-deriving them from the accumulated angle every step:
+// 4 operations + a short polynomial per step instead of a full range-reduced sincos.  The error of the pair grows
+// like that of the FP32 yaw accumulation it replaces (~1e-7 per step; measured against the FP64 oracle in
+// tests/test_oracle.py).
+MPPI_HD void rotate(float &c, float &s, float cd, float sd) {
+  float c2 = fmaf(c, cd, -(s * sd));
+  float s2 = fmaf(s, cd, c * sd);
+  c = c2;
+  s = s2;
+}
+template <bool SMALL = false>
+MPPI_HD void rotate_by(float &c, float &s, float angle) {
+  float sd, cd;
+  sincos_increment<SMALL>(angle, sd, cd);
+  rotate(c, s, cd, sd);
+}
+
+// True when every per-step angle of this solve is provably inside the polynomial ranges: the controls are clamped
+// to [u_min, u_max], and |clamp(v) * dt| <= max(|u_min|, |u_max|) * dt holds in FP32 as well (rounding is
+// monotonic).  The kernels then run the instantiation without the range tests -- same bits as the tested path.
+MPPI_HD bool angles_are_small(const SolveParams &P) {
+  bool ok = true;
+  auto bound = [&](int u) { return fmaxf(fabsf(P.u_min[u]), fabsf(P.u_max[u])); };
+  ok = ok && (bound(1) * fabsf(P.dt) <= kSmallIncrement);
+  if (P.model != kDiffDrive) ok = ok && (bound(2) <= kSmallAngle);
+  if (P.model == kFullBody) ok = ok && (bound(3) * fabsf(P.dt) <= kSmallIncrement) && (bound(4) * fabsf(P.dt) <= kSmallIncrement);
+  return ok;  // any NaN parameter compares false
 }
 
 // atan2 in the FP32 contract (same bits on host and device): octant reduction + the classic single-precision
@@ -162,27 +252,57 @@ MPPI_HD float min_dist2_literal(float x, float y, const Win &win, int T, int *ar
   return best;
 }
 
-// planar part of predict_NextState (DD:106-108); heading = yaw (DD) or yaw + steer/direction (SD:122, FB:447)
-MPPI_HD void step_pose(float &x, float &y, float &yaw, float v, float w, float heading, float dt) {
-  float s, c;
-  sincos_f32(heading, s, c);
-  x = fmaf(v * c, dt, x);
-  y = fmaf(v * s, dt, y);
-  yaw = fmaf(w, dt, yaw);
+// Orientation of one sample as the kernels carry it: the angles themselves (debug taps only -- dead code in the
+// production kernel) and the cos / sin pairs advanced by rotate_by().
+template <int MODEL>
+struct Attitude {
+  float yaw, cy, sy;
+  float roll, cr, sr;    // full body only
+  float pitch, cp, sp;   // full body only
+  MPPI_HD void init(const float *state0) {
+    yaw = state0[2];
+    sincos_f32(yaw, sy, cy);
+    roll = pitch = 0.f;
+    cr = cp = 1.f;
+    sr = sp = 0.f;
+    if (MODEL == kFullBody) {
+      roll = state0[3];
+      pitch = state0[4];
+      sincos_f32(roll, sr, cr);
+      sincos_f32(pitch, sp, cp);
+    }
+  }
+};
+
+// predict_NextState (DD:104-109 / SD:120-125 / FB:445-452) for one sample; u = controls of this step.
+// Heading = yaw (DD) or yaw + steer/direction (SD:122, FB:447): cos/sin(yaw + d) by the addition theorem from
+// the carried (cos yaw, sin yaw) and (sd, cd) = sincos_f32(d), which the caller shares with the ZMP model
+// (FB:473-474); (sd, cd) is ignored for DD.
+template <int MODEL, bool SMALL = false>
+MPPI_HD void step_state(float &x, float &y, Attitude<MODEL> &a, const float *u, float dt, float sd, float cd) {
+  float ch = a.cy, sh = a.sy;
+  if (MODEL != kDiffDrive) rotate(ch, sh, cd, sd);
+  x = fmaf(u[0] * ch, dt, x);
+  y = fmaf(u[0] * sh, dt, y);
+  a.yaw = fmaf(u[1], dt, a.yaw);
+  rotate_by<SMALL>(a.cy, a.sy, u[1] * dt);
+  if (MODEL == kFullBody) {
+    a.roll = fmaf(u[3], dt, a.roll);    // FB:450
+    a.pitch = fmaf(u[4], dt, a.pitch);  // FB:451
+    rotate_by<SMALL>(a.cr, a.sr, u[3] * dt);
+    rotate_by<SMALL>(a.cp, a.sp, u[4] * dt);
+  }
 }
 
 // zmp_y of FB:468-486 + FB:597-603 for one (sample, t):
 //   CoM = (b sin pitch, -b sin roll, b cos pitch cos roll);  a = (ax, ay, 0);  HGdot = I (omega+ - omega)/dt
 //   zmp_y = CoM_y + CoM_z * ay / g_z - HGdot_x / (m g_z)
 // zmp_x (unused by the cost) is returned for tests:  zmp_x = CoM_x + CoM_z * ax / g_z + HGdot_y / (m g_z)
-MPPI_HD void zmp_model(const SolveParams &P, float v0, float v1, float w0, float dir0, float rv0, float rv1,
-                       float pv0, float pv1, float roll0, float pitch0, float &zmp_x, float &zmp_y) {
+// (sd, cd) = sin/cos of direction_[t]; (sr, cr), (sp, cp) = sin/cos of roll_[t], pitch_[t].
+MPPI_HD void zmp_model(const SolveParams &P, float v0, float v1, float w0, float sd, float cd, float rv0, float rv1,
+                       float pv0, float pv1, float sr, float cr, float sp, float cp, float &zmp_x, float &zmp_y) {
   float drive_accel = (v1 - v0) * P.inv_dt;
   float ac = v0 * w0;
-  float sd, cd, sr, cr, sp, cp;
-  sincos_f32(dir0, sd, cd);
-  sincos_f32(roll0, sr, cr);
-  sincos_f32(pitch0, sp, cp);
   float ax = drive_accel * cd - ac * sd;
   float ay = fmaf(drive_accel, sd, ac * cd);
   float hgd_x = P.ixx * ((rv1 - rv0) * P.inv_dt);
@@ -230,9 +350,9 @@ MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, fl
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   const int T = P.T;
   const int Tc = num_cost_states(MODEL, T);
-  float x = state0[0], y = state0[1], yaw = state0[2];
-  float roll = MODEL == kFullBody ? state0[3] : 0.f;
-  float pitch = MODEL == kFullBody ? state0[4] : 0.f;
+  float x = state0[0], y = state0[1];
+  Attitude<MODEL> att;
+  att.init(state0);
   CostAcc acc;
   float cur[U], nxt[U];
 #pragma unroll
@@ -249,7 +369,7 @@ MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, fl
   };
   if (T > 1) draw(0, cur);
   for (int t = 0; t < T; ++t) {
-    sink.state(t, x, y, yaw, roll, pitch);
+    sink.state(t, x, y, att.yaw, att.roll, att.pitch);
     const bool has_step = t < T - 1;
     if (MODEL == kFullBody && t + 1 < T - 1) draw(t + 1, nxt);
     if (t < Tc) {
@@ -258,6 +378,8 @@ MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, fl
       sink.nearest(t, arg, d2);
       acc.path += d2;
     }
+    float sd = 0.f, cd = 1.f;  // sin / cos of steer_[t] / direction_[t]
+    if (MODEL != kDiffDrive && has_step) sincos_f32(cur[2], sd, cd);
     if (MODEL != kFullBody) {
       if (has_step) {
         float dv = cur[0] - P.v_ref;
@@ -267,7 +389,8 @@ MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, fl
       float dv = cur[0] - P.v_ref;
       acc.vel = fmaf(dv, dv, acc.vel);
       float zx, zy;
-      zmp_model(P, cur[0], nxt[0], cur[1], cur[2], cur[3], nxt[3], cur[4], nxt[4], roll, pitch, zx, zy);
+      zmp_model(P, cur[0], nxt[0], cur[1], sd, cd, cur[3], nxt[3], cur[4], nxt[4], att.sr, att.cr, att.sp, att.cp, zx,
+                zy);
       sink.zmp(t, zx, zy);
       acc.zmp = fmaf(zy, zy, acc.zmp);
       float dr = nxt[3] - cur[3];
@@ -275,12 +398,7 @@ MPPI_HD float rollout_cost_literal(const SolveParams &P, const float *state0, fl
       if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
     }
     if (has_step) {
-      float heading = MODEL == kDiffDrive ? yaw : yaw + cur[2];
-      step_pose(x, y, yaw, cur[0], cur[1], heading, P.dt);
-      if (MODEL == kFullBody) {
-        roll = fmaf(cur[3], P.dt, roll);    // FB:450
-        pitch = fmaf(cur[4], P.dt, pitch);  // FB:451
-      }
+      step_state<MODEL>(x, y, att, cur, P.dt, sd, cd);
       if (MODEL == kFullBody) {
 #pragma unroll
         for (int u = 0; u < U; ++u) cur[u] = nxt[u];

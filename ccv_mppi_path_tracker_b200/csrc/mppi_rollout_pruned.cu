@@ -22,6 +22,8 @@
 // Blackwell's packed FP32 pipe (sub/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2, two window points per instruction,
 // the same IEEE roundings per element as mppi::dist2) and the 3-input FMNMX3.  States outside the grid scan the
 // whole window.  min() is exact and order independent, so the accumulated path cost has the literal scan's bits.
+#include <cuda.h>
+
 #include "mppi_device.cuh"
 
 namespace mppi {
@@ -73,41 +75,58 @@ __device__ __forceinline__ float lds32_volatile(unsigned addr) {  // ring slots 
   return v;
 }
 
-// min over the window pairs [q0, q0 + 2*n2) of min(d2, best); pairs = {x0, x1, y0, y1}.  Two pairs (four window
-// points) per iteration; scanning a few points more than the candidate range is always safe (they are window
-// points too), so the range is rounded up instead of predicated.
-__device__ __forceinline__ float scan_pairs(unsigned pairs_s, int q0, int n2, float x, float y, float best) {
+// Cell entry (K0 -> K2): low half = byte offset of the first window pair of the candidate range inside the shared
+// pair array, high half = byte length of the range, a non-zero multiple of 32 (two pairs = four window points per
+// scan iteration).  T <= 4096 keeps both below 2^16.
+__host__ __device__ __forceinline__ uint32_t cell_entry(int first_pair, int iterations) {
+  return (uint32_t)first_pair * 16u | ((uint32_t)iterations * 32u) << 16;
+}
+
+// min over the window pairs of one cell entry of min(d2, 1e4); pairs = {x0, x1, y0, y1}.  Two pairs (four window
+// points) per iteration, at least one iteration; scanning a few points more than the candidate range is always
+// safe (they are window points too), so the range is rounded up instead of predicated.
+__device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float x, float y) {
   const u64 xx = pack2(x, x), yy = pack2(y, y);
-  unsigned p = pairs_s + (unsigned)q0 * 16u;
+  unsigned p = pairs_s + (e & 0xFFFFu);
+  const unsigned p_end = p + (e >> 16);
+  float best = kDist2Cap;
 #pragma unroll 1
-  for (int k = 0; k < n2; ++k, p += 32u) {
+  do {
     const float4 a = lds128(p), b = lds128(p + 16u);
     float a0, a1, b0, b1;
     unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
     unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
     best = min3f(best, a0, a1);
     best = min3f(best, b0, b1);
-  }
+    p += 32u;
+  } while (p != p_end);
   return best;
 }
 
 struct GridView {
-  const uint32_t *cells;  // [ny + 2][nx + 2]: first pair | (number of 2-pair iterations) << 16; the one-cell
-                          // border ring says "scan the whole window" (positions outside the grid are clamped to it)
+  const uint32_t *cells;  // [ny + 2][nx + 2] cell entries; the one-cell border ring says "scan the whole window"
+                          // (positions outside the grid are clamped to it)
   float inv_h, cx, cy;    // table index = floor(fma(x, inv_h, cx)), floor(fma(y, inv_h, cy)) (border included)
-  int nx2, ny2;           // nx + 2, ny + 2
+  int nx2, ixmax, iymax;  // nx + 2, nx + 1, ny + 1
 };
+
+// clamp(v, 0, hi) in one instruction: max(min(v, hi), 0)
+__device__ __forceinline__ int clamp0(int v, int hi) {
+  int r;
+  asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(hi));
+  return r;
+}
 
 // Candidate range of the cell that contains (x, y).  Branch-free lookup: the float->int conversion saturates, the
 // clamp sends everything outside the grid to the border ring.
 __device__ __forceinline__ uint32_t grid_cell(const GridView &g, float x, float y) {
-  const int ix = min(max(__float2int_rd(fmaf(x, g.inv_h, g.cx)), 0), g.nx2 - 1);
-  const int iy = min(max(__float2int_rd(fmaf(y, g.inv_h, g.cy)), 0), g.ny2 - 1);
+  const int ix = clamp0(__float2int_rd(fmaf(x, g.inv_h, g.cx)), g.ixmax);
+  const int iy = clamp0(__float2int_rd(fmaf(y, g.inv_h, g.cy)), g.iymax);
   return __ldg(g.cells + (iy * g.nx2 + ix));
 }
 // Exact min_j min(d2(p, r_j), 1e4) over the whole window, given the cell entry of (x, y).
 __device__ __forceinline__ float min_dist2_cell(uint32_t e, unsigned pairs_s, float x, float y) {
-  return scan_pairs(pairs_s, (int)(e & 0xFFFFu), (int)(e >> 16), x, y, kDist2Cap);
+  return scan_pairs(pairs_s, e, x, y);
 }
 
 // 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, so the normals of future control
@@ -202,7 +221,7 @@ __global__ void __launch_bounds__(128)
   if (cell >= nx2 * ny2) return;
   const int tx = cell % nx2, ty = cell / nx2;
   if (tx == 0 || ty == 0 || tx == nx2 - 1 || ty == ny2 - 1) {  // border ring: the whole (padded) window
-    cells[(size_t)robot * max_cells + cell] = (uint32_t)(((T + 1) / 2 + 1) / 2) << 16;
+    cells[(size_t)robot * max_cells + cell] = cell_entry(0, ((T + 1) / 2 + 1) / 2);
     return;
   }
   const int ix = tx - 1, iy = ty - 1;
@@ -251,7 +270,7 @@ __global__ void __launch_bounds__(128)
     q0 = lo >> 1;
     n2 = ((hi >> 1) - q0 + 2) >> 1;
   }
-  cells[(size_t)robot * max_cells + cell] = (uint32_t)q0 | ((uint32_t)n2 << 16);
+  cells[(size_t)robot * max_cells + cell] = cell_entry(q0, n2);
 }
 
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
@@ -272,6 +291,277 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
 size_t pruned_smem_bytes(int T, int planes, int U) {
   // window pairs {x0,x1,y0,y1} x (ceil(T/2) + 1 pad) | ring of normals [kRing][U][128] | nominal padded by two steps
   return sizeof(float4) * (size_t)((T + 1) / 2 + 1) + sizeof(float) * ((size_t)kRing * U * 128 + (size_t)planes + 2 * U);
+}
+
+// What one thread needs besides its sample index (all CTA-uniform)
+struct ThreadCtx {
+  const SolveParams *sP;    // shared copy of the per-solve constants
+  GridView gv;
+  unsigned pairs_s, ring_s, nom_s;  // shared-window addresses: window pairs, this thread's ring column, warm start
+  const float *e_ptr;       // normals of (step 0, control 0) of this sample (cp.async ring only)
+  const float *st;          // state record of the robot
+  size_t Kp;
+  int T;
+};
+
+// Registers of one rollout: pose, carried cos/sin pairs, cost accumulators, the candidate range of the current state.
+template <int MODEL, bool SMALL>
+struct Rollout {
+  static constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
+  const SolveParams &sP;
+  const GridView &gv;
+  const unsigned pairs_s, nom_s;
+  float x, y;
+  Attitude<MODEL> att;  // cos / sin of yaw (roll, pitch) carried through the horizon (mppi_math.h)
+  CostAcc acc;
+  uint32_t cell;
+  float sigma, dt, v_ref;
+  bool steer_off;
+  float lo[U], hi[U];
+
+  __device__ __forceinline__ Rollout(const ThreadCtx &cx)
+      : sP(*cx.sP), gv(cx.gv), pairs_s(cx.pairs_s), nom_s(cx.nom_s) {
+    x = cx.st[0];
+    y = cx.st[1];
+    att.init(cx.st);
+    sigma = sP.sigma;
+    dt = sP.dt;
+    v_ref = sP.v_ref;
+    steer_off = MODEL == kFullBody && sP.steer_off;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      lo[u] = sP.u_min[u];
+      hi[u] = sP.u_max[u];
+    }
+    cell = grid_cell(gv, x, y);
+  }
+  // sampling (D5) of step t: normals at shared address src + u * row_bytes; past the last step the result is never
+  // used (s_nom is padded)
+  __device__ __forceinline__ void make(int t, unsigned src, unsigned row_bytes, float *dst) const {
+    const unsigned nom = nom_s + (unsigned)(t * U) * 4u;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      dst[u] = sample_control(lds32_volatile(src + u * row_bytes), sigma, lds32(nom + u * 4u), lo[u], hi[u]);
+    if (steer_off) dst[2] = 0.f;  // FB:517
+  }
+  // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
+  // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
+  // current state, loaded one iteration earlier).
+  __device__ __forceinline__ void advance(const float *cur, const float *nxt) {
+    const float x0 = x, y0 = y;
+    const float sr0 = att.sr, cr0 = att.cr, sp0 = att.sp, cp0 = att.cp;
+    float sd = 0.f, cd = 1.f;
+    if (MODEL != kDiffDrive) sincos_f32<SMALL>(cur[2], sd, cd);
+    step_state<MODEL, SMALL>(x, y, att, cur, dt, sd, cd);
+    const uint32_t cell_next = grid_cell(gv, x, y);
+    acc.path += min_dist2_cell(cell, pairs_s, x0, y0);
+    cell = cell_next;
+    const float dv = cur[0] - v_ref;
+    acc.vel = fmaf(dv, dv, acc.vel);
+    if (MODEL == kFullBody) {
+      float zx, zy;
+      zmp_model(sP, cur[0], nxt[0], cur[1], sd, cd, cur[3], nxt[3], cur[4], nxt[4], sr0, cr0, sp0, cp0, zx, zy);
+      acc.zmp = fmaf(zy, zy, acc.zmp);
+      const float dr = nxt[3] - cur[3];
+      acc.droll = fmaf(dr, dr, acc.droll);
+      if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
+    }
+  }
+  __device__ __forceinline__ float finish(const float *st) {
+    if (MODEL != kFullBody) acc.path += min_dist2_cell(cell, pairs_s, x, y);  // state T-1: path term only (D1)
+    float yaw0_err = 0.f;
+    if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
+      const float4 w01 = lds128(pairs_s);
+      yaw0_err = st[2] - yaw_ref0_f32(w01.x, w01.z, w01.y, w01.w);
+    }
+    return combine_cost(sP, acc, yaw0_err);
+  }
+};
+
+// The rollout of one sample, normals streamed by the per-thread cp.async ring.
+// SMALL = angles_are_small(): the instantiation without the per-step angle range tests.
+template <int MODEL, bool SMALL>
+__device__ __forceinline__ float rollout_thread(const ThreadCtx &cx) {
+  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
+  constexpr unsigned kSlotBytes = U * 128 * 4;
+  Rollout<MODEL, SMALL> r(cx);
+  const unsigned ring_s = cx.ring_s;
+  const int T = cx.T;
+  const int steps = T - 1;
+  // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
+  // looks at the last two states, FB:409)
+  const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
+  float ca[U], cb[U];  // controls of the current and the next step (roles alternate, no register moves)
+  // normals of control step t: eps[(t*U + u)*Kp + i], streamed through this thread's column of the ring
+  const size_t Kp = cx.Kp;
+  const size_t step_stride = (size_t)U * Kp;
+  const float *e_ptr = cx.e_ptr;
+  // start the copy of step t into ring slot `slot` (nothing past the last step); one commit group per step
+  auto issue = [&](int t, unsigned slot) {
+    if (t < steps) {
+      const unsigned dst = ring_s + slot * kSlotBytes;
+#pragma unroll
+      for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 512u, e_ptr + (size_t)u * Kp);
+      e_ptr += step_stride;
+    }
+    cp_async_commit();
+  };
+  auto make = [&](int t, unsigned slot, float *dst) { r.make(t, ring_s + slot * kSlotBytes, 512u, dst); };
+#pragma unroll
+  for (int k = 0; k < kRing; ++k) issue(k, (unsigned)k);
+  cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
+  make(0, 0u, ca);
+  make(1, 1u, cb);
+  // Iteration t consumes step t (cur) and t+1 (nxt), then refills: step t+4 goes into slot t%4 (held step t,
+  // consumed), step t+2 -- issued two iterations ago -- is sampled from slot (t+2)%4 into the register set that
+  // held step t.  Unrolled by the ring size so that slots and register roles are compile-time constants.
+  int t = 0;
+  for (; t + kRing <= n_iter; t += kRing) {
+    r.advance(ca, cb);
+    issue(t + 4, 0u);
+    cp_async_wait<2>();
+    make(t + 2, 2u, ca);
+    r.advance(cb, ca);
+    issue(t + 5, 1u);
+    cp_async_wait<2>();
+    make(t + 3, 3u, cb);
+    r.advance(ca, cb);
+    issue(t + 6, 2u);
+    cp_async_wait<2>();
+    make(t + 4, 0u, ca);
+    r.advance(cb, ca);
+    issue(t + 7, 3u);
+    cp_async_wait<2>();
+    make(t + 5, 1u, cb);
+  }
+  for (; t < n_iter; ++t) {  // at most kRing - 1 iterations; (ca, cb) = (step t, step t+1) on entry
+    r.advance(ca, cb);
+    issue(t + 4, (unsigned)(t & 3));
+    cp_async_wait<2>();
+#pragma unroll
+    for (int u = 0; u < U; ++u) ca[u] = cb[u];
+    make(t + 2, (unsigned)((t + 2) & 3), cb);
+  }
+  return r.finish(cx.st);
+}
+
+// ---- TMA ring -------------------------------------------------------------------------------------------------
+// One ring PER WARP: a stage is the tile {32 samples of the warp} x {kStageSteps control steps x U planes} of the
+// plane-major noise tensor, fetched by ONE cp.async.bulk.tensor issued by lane 0 and landing as [row][32] floats
+// (128 B rows, conflict-free column reads).  Completion is signalled on the stage's mbarrier (expect-tx bytes);
+// a slot is refilled after __syncwarp() -- every lane has then consumed its column into registers.  Warps never
+// wait for each other.  Per control step this costs ~2 issue slots instead of the ~14 of the per-thread LDGSTS
+// ring (address arithmetic, predicates, commit / wait groups).
+constexpr int kStageSteps = 4;
+constexpr int kStages = 3;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+struct TmaCtx {
+  const CUtensorMap *map;
+  unsigned ring_s;  // this warp's ring: kStages tiles of kStageSteps * U rows x 128 B
+  unsigned bar_s;   // this warp's kStages mbarriers
+  int c0;           // first sample of the warp
+  int row0;         // robot * planes
+};
+
+template <int MODEL, bool SMALL>
+__device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const TmaCtx &tc) {
+  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
+  constexpr int kRows = kStageSteps * U;
+  constexpr unsigned kTileBytes = kRows * 128u;
+  constexpr unsigned kStepBytes = U * 128u;
+  Rollout<MODEL, SMALL> r(cx);
+  const int T = cx.T;
+  const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
+  // tiles 0 .. n_tiles-1 cover control steps 0 .. n_iter (the last one may lie past the end: sampled, never used;
+  // rows beyond the tensor are zero-filled by the TMA unit), so every make() below has a tile to wait for -- and
+  // every tile that is fetched is also waited for before the thread returns (no copy in flight at CTA exit)
+  const int n_tiles = n_iter / kStageSteps + 1;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned col = tc.ring_s + lane * 4u;
+  auto fetch = [&](int tile, unsigned slot) {
+    if (tile < n_tiles) {  // warp-uniform
+      if (elect_one()) {
+        const unsigned bar = tc.bar_s + slot * 8u;
+        mbar_expect_tx(bar, kTileBytes);
+        tma_load_2d(tc.ring_s + slot * kTileBytes, tc.map, tc.c0, tc.row0 + tile * kRows, bar);
+      }
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kStages; ++k) fetch(k, (unsigned)k);
+  float ca[U], cb[U];
+  unsigned slot = 0, parity = 0;
+  mbar_wait(tc.bar_s, 0);
+  r.make(0, col, 128u, ca);
+  int t = 0;
+  for (int tile = 0; t + kStageSteps <= n_iter; t += kStageSteps, ++tile) {
+    const unsigned base = col + slot * kTileBytes;
+    r.make(t + 1, base + kStepBytes, 128u, cb);
+    r.advance(ca, cb);
+    r.make(t + 2, base + 2 * kStepBytes, 128u, ca);
+    r.advance(cb, ca);
+    r.make(t + 3, base + 3 * kStepBytes, 128u, cb);
+    r.advance(ca, cb);
+    // every lane has read its column of this slot: refill it with the tile kStages ahead, then move on
+    __syncwarp();
+    fetch(tile + kStages, slot);
+    if (++slot == kStages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+    mbar_wait(tc.bar_s + slot * 8u, parity);
+    r.make(t + 4, col + slot * kTileBytes, 128u, ca);
+    r.advance(cb, ca);
+  }
+  {  // at most kStageSteps - 1 iterations, all inside the current tile; ca = step t on entry
+    const unsigned base = col + slot * kTileBytes;
+    for (int k = 1; t < n_iter; ++t, ++k) {
+      r.make(t + 1, base + k * kStepBytes, 128u, cb);
+      r.advance(ca, cb);
+#pragma unroll
+      for (int u = 0; u < U; ++u) ca[u] = cb[u];
+    }
+  }
+  return r.finish(cx.st);
 }
 
 #ifndef MPPI_K2_MINBLOCKS
@@ -313,127 +603,145 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
   if (i < K) {
     const uint32_t *cp = cells + (size_t)robot * max_cells;
     asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
-    const GridView gv{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.ny + 2};
-    unsigned pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
-    unsigned ring_s = (unsigned)__cvta_generic_to_shared(s_eps + threadIdx.x);
-    unsigned nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
+    ThreadCtx cx;
+    cx.sP = &sP;
+    cx.gv = GridView{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.nx + 1, s_gh.ny + 1};
+    cx.pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
+    cx.ring_s = (unsigned)__cvta_generic_to_shared(s_eps + threadIdx.x);
+    cx.nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
     // pin the three shared-window addresses in registers (otherwise they are re-derived from SR_CgaCtaId per step)
-    asm volatile("" : "+r"(pairs_s), "+r"(ring_s), "+r"(nom_s));
-    constexpr unsigned kSlotBytes = U * 128 * 4;
-    const float *st = state + (size_t)robot * 8;
-    const int steps = T - 1;
-    // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
-    // looks at the last two states, FB:409)
-    const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
-    float x = st[0], y = st[1], yaw = st[2];
-    float roll = MODEL == kFullBody ? st[3] : 0.f;
-    float pitch = MODEL == kFullBody ? st[4] : 0.f;
-    const float sigma = sP.sigma, dt = sP.dt, v_ref = sP.v_ref;
-    const bool steer_off = MODEL == kFullBody && sP.steer_off;
-    float lo[U], hi[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      lo[u] = sP.u_min[u];
-      hi[u] = sP.u_max[u];
-    }
-    CostAcc acc;
-    float ca[U], cb[U];  // controls of the current and the next step (roles alternate, no register moves)
-    // normals of control step t: eps[(t*U + u)*Kp + i], streamed through this thread's column of the ring
-    const size_t step_stride = (size_t)U * Kp;
-    const float *e_ptr = eps + (size_t)robot * planes * Kp + i;
-    // start the copy of step t into ring slot `slot` (nothing past the last step); one commit group per step
-    auto issue = [&](int t, unsigned slot) {
-      if (t < steps) {
-        const unsigned dst = ring_s + slot * kSlotBytes;
-#pragma unroll
-        for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 512u, e_ptr + (size_t)u * Kp);
-        e_ptr += step_stride;
-      }
-      cp_async_commit();
-    };
-    // sampling (D5) of step t from ring slot `slot`; past the last step the result is never used (s_nom is padded)
-    auto make = [&](int t, unsigned slot, float *dst) {
-      const unsigned src = ring_s + slot * kSlotBytes;
-      const unsigned nom = nom_s + (unsigned)(t * U) * 4u;
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        dst[u] = sample_control(lds32_volatile(src + u * 512u), sigma, lds32(nom + u * 4u), lo[u], hi[u]);
-      if (steer_off) dst[2] = 0.f;  // FB:517
-    };
-    // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
-    // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
-    // current state, loaded one iteration earlier).
-    uint32_t cell = grid_cell(gv, x, y);
-    auto advance = [&](const float *cur, const float *nxt) {
-      const float x0 = x, y0 = y, roll0 = roll, pitch0 = pitch;
-      const float heading = MODEL == kDiffDrive ? yaw : yaw + cur[2];
-      step_pose(x, y, yaw, cur[0], cur[1], heading, dt);
-      if (MODEL == kFullBody) {
-        roll = fmaf(cur[3], dt, roll);
-        pitch = fmaf(cur[4], dt, pitch);
-      }
-      const uint32_t cell_next = grid_cell(gv, x, y);
-      acc.path += min_dist2_cell(cell, pairs_s, x0, y0);
-      cell = cell_next;
-      const float dv = cur[0] - v_ref;
-      acc.vel = fmaf(dv, dv, acc.vel);
-      if (MODEL == kFullBody) {
-        float zx, zy;
-        zmp_model(sP, cur[0], nxt[0], cur[1], cur[2], cur[3], nxt[3], cur[4], nxt[4], roll0, pitch0, zx, zy);
-        acc.zmp = fmaf(zy, zy, acc.zmp);
-        const float dr = nxt[3] - cur[3];
-        acc.droll = fmaf(dr, dr, acc.droll);
-        if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
-      }
-    };
-#pragma unroll
-    for (int k = 0; k < kRing; ++k) issue(k, (unsigned)k);
-    cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
-    make(0, 0u, ca);
-    make(1, 1u, cb);
-    // Iteration t consumes step t (cur) and t+1 (nxt), then refills: step t+4 goes into slot t%4 (held step t,
-    // consumed), step t+2 -- issued two iterations ago -- is sampled from slot (t+2)%4 into the register set that
-    // held step t.  Unrolled by the ring size so that slots and register roles are compile-time constants.
-    int t = 0;
-    for (; t + kRing <= n_iter; t += kRing) {
-      advance(ca, cb);
-      issue(t + 4, 0u);
-      cp_async_wait<2>();
-      make(t + 2, 2u, ca);
-      advance(cb, ca);
-      issue(t + 5, 1u);
-      cp_async_wait<2>();
-      make(t + 3, 3u, cb);
-      advance(ca, cb);
-      issue(t + 6, 2u);
-      cp_async_wait<2>();
-      make(t + 4, 0u, ca);
-      advance(cb, ca);
-      issue(t + 7, 3u);
-      cp_async_wait<2>();
-      make(t + 5, 1u, cb);
-    }
-    for (; t < n_iter; ++t) {  // at most kRing - 1 iterations; (ca, cb) = (step t, step t+1) on entry
-      advance(ca, cb);
-      issue(t + 4, (unsigned)(t & 3));
-      cp_async_wait<2>();
-#pragma unroll
-      for (int u = 0; u < U; ++u) ca[u] = cb[u];
-      make(t + 2, (unsigned)((t + 2) & 3), cb);
-    }
-    if (MODEL != kFullBody) acc.path += min_dist2_cell(cell, pairs_s, x, y);  // state T-1: path term only (D1)
-    float yaw0_err = 0.f;
-    if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
-      const float4 w01 = s_pairs[0];
-      yaw0_err = st[2] - yaw_ref0_f32(w01.x, w01.z, w01.y, w01.w);
-    }
-    c = combine_cost(sP, acc, yaw0_err);
+    asm volatile("" : "+r"(cx.pairs_s), "+r"(cx.ring_s), "+r"(cx.nom_s));
+    cx.e_ptr = eps + (size_t)robot * planes * Kp + i;
+    cx.st = state + (size_t)robot * 8;
+    cx.Kp = (size_t)Kp;
+    cx.T = T;
+    // CTA-uniform choice of the instantiation (per-solve constants: dt and the control bounds)
+    c = angles_are_small(sP) ? rollout_thread<MODEL, true>(cx) : rollout_thread<MODEL, false>(cx);
     cost[(size_t)robot * K + i] = c;
   }
   block_min_to_global(c, i < K, cmin + robot, s_red);
 }
 
+// K2 with the TMA ring.  Same prologue as above; dynamic shared memory = ring [4 warps][kStages][rows][32] (1 KB
+// aligned) | window pairs | warm start.  Whole warps run the rollout (the refill needs all 32 lanes at the
+// __syncwarp); lanes past K compute on zero / padding normals and are masked at the store.
+size_t pruned_tma_smem_bytes(int T, int planes, int U) {
+  return (size_t)4 * kStages * kStageSteps * U * 128 + sizeof(float4) * (size_t)((T + 1) / 2 + 1) +
+         sizeof(float) * ((size_t)planes + 2 * U);
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
+    rollout_cost_tma_kernel(const __grid_constant__ CUtensorMap eps_map, const SolveHeader *__restrict__ hdr,
+                            const float *__restrict__ nominal, const float *__restrict__ window,
+                            const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
+                            const uint32_t *__restrict__ cells, float *__restrict__ cost,
+                            unsigned int *__restrict__ cmin, int K, int planes, int win_stride, int T, int max_cells) {
+  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
+  constexpr int kWarpRingBytes = kStages * kStageSteps * U * 128;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ SolveParams sP;
+  __shared__ float s_red[32];
+  __shared__ GridHeader s_gh;
+  __shared__ __align__(8) unsigned long long s_bar[4 * kStages];
+  const int robot = blockIdx.y;
+  const int NP = (T + 1) / 2;
+  float4 *s_pairs = reinterpret_cast<float4 *>(smem_raw + 4 * kWarpRingBytes);
+  float *s_nom = reinterpret_cast<float *>(s_pairs + NP + 1);
+
+  const float *g_win = window + (size_t)robot * win_stride;
+  load_params_to_shared(&sP, hdr);
+  if (threadIdx.x == 0) s_gh = ghdr[robot];
+  if (threadIdx.x < 4 * kStages) mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[threadIdx.x]), 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int q = threadIdx.x; q < NP + 1; q += blockDim.x) {
+    const int j0 = min(2 * q, T - 1), j1 = min(2 * q + 1, T - 1);
+    s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
+  }
+  for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
+    s_nom[j] = j < planes ? nominal[(size_t)robot * planes + j] : 0.f;
+  __syncthreads();
+
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform (TMA operands live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int warp_first = blockIdx.x * blockDim.x + warp * 32;
+  float c = 0.f;
+  if (warp_first < K) {  // warp-uniform
+    const uint32_t *cp = cells + (size_t)robot * max_cells;
+    asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
+    ThreadCtx cx;
+    cx.sP = &sP;
+    cx.gv = GridView{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.nx + 1, s_gh.ny + 1};
+    cx.pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
+    cx.nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
+    cx.ring_s = 0;
+    cx.e_ptr = nullptr;
+    cx.st = state + (size_t)robot * 8;
+    cx.Kp = 0;
+    cx.T = T;
+    TmaCtx tc;
+    tc.map = &eps_map;
+    tc.ring_s = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(warp * kWarpRingBytes);
+    tc.bar_s = (unsigned)__cvta_generic_to_shared(&s_bar[warp * kStages]);
+    tc.c0 = warp_first;
+    tc.row0 = robot * planes;
+    asm volatile("" : "+r"(cx.pairs_s), "+r"(cx.nom_s), "+r"(tc.ring_s), "+r"(tc.bar_s));
+    c = angles_are_small(sP) ? rollout_thread_tma<MODEL, true>(cx, tc) : rollout_thread_tma<MODEL, false>(cx, tc);
+    if (i < K) cost[(size_t)robot * K + i] = c;
+  }
+  block_min_to_global(c, i < K, cmin + robot, s_red);
+}
+
+// Tensor map of the noise tensor for the TMA ring: 2-D {Kp samples, R * planes rows} of f32, box {32, kStageSteps*U}.
+// cuTensorMapEncodeTiled is taken from the driver through the runtime (no link-time dependency on libcuda).
+cudaError_t make_eps_tensor_map(DeviceState &d) {
+  d.eps_map_valid = false;
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {(cuuint64_t)d.Kp, (cuuint64_t)d.R * (cuuint64_t)d.planes};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d.Kp * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)(kStageSteps * d.U)};
+  const cuuint32_t estride[2] = {1u, 1u};
+  CUresult r = ((EncodeFn)fn)(&d.eps_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.eps, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  d.eps_map_valid = true;
+  return cudaSuccess;
+}
+
+cudaError_t launch_rollout_cost_tma(const DeviceState &d, cudaStream_t s) {
+  dim3 grid((d.K + 127) / 128, d.R);
+  const size_t smem = pruned_tma_smem_bytes(d.T, d.planes, d.U);
+#define MPPI_LAUNCH_TMA(M)                                                                                       \
+  do {                                                                                                           \
+    if (smem > 48 * 1024) {                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(rollout_cost_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                           \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    rollout_cost_tma_kernel<M><<<grid, 128, smem, s>>>(d.eps_map, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, \
+                                                       d.grid_cells, d.cost, d.cmin, d.K, d.planes, d.win_stride, \
+                                                       d.T, d.grid_max_cells);                                   \
+  } while (0)
+  switch (d.model) {
+    case kDiffDrive: MPPI_LAUNCH_TMA(kDiffDrive); break;
+    case kSteering: MPPI_LAUNCH_TMA(kSteering); break;
+    default: MPPI_LAUNCH_TMA(kFullBody); break;
+  }
+#undef MPPI_LAUNCH_TMA
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
+  if (d.eps_map_valid && d.k2_ring == 1) return launch_rollout_cost_tma(d, s);
   dim3 grid((d.K + 127) / 128, d.R);
   const size_t smem = pruned_smem_bytes(d.T, d.planes, d.U);
 #define MPPI_LAUNCH_PRUNED(M)                                                                                    \
@@ -458,7 +766,8 @@ cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
 
 // worth it only for windows of more than a couple of dozen points; the 16-bit pair fields bound T
 bool pruned_scan_supported(int T, int planes) {
-  return T >= 24 && T <= 65534 && pruned_smem_bytes(T, planes, kMaxControls) <= 200 * 1024;
+  return T >= 24 && T <= 4096 && pruned_smem_bytes(T, planes, kMaxControls) <= 200 * 1024 &&
+         pruned_tma_smem_bytes(T, planes, kMaxControls) <= 200 * 1024;
 }
 
 }  // namespace mppi
