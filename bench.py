@@ -155,22 +155,47 @@ def synthetic_inputs(model, R, course_length, seed=0):
     return path_list, states
 
 
-def cpu_baseline_run(model, T, course_length, seconds_budget=12.0):
-    """FP64 oracle (port of the reference loops) on the host cores: all threads, bounded K sample."""
-    import oracle
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def _cpu_case(model, T, course_length):
     from ccv_mppi_path_tracker_b200 import params, paths
     p = params.node_params(model, launch=True, horizon=T, **({"roll_off": False} if model == "full_body" else {}))
-    sp = params.solve_params(model, p)
     kw = dict(params.LAUNCH_PATH[model])
     kw["course_length"] = course_length
-    path = paths.sin_path(**kw)
-    S = params.NUM_STATES[model]
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:  # noqa: BLE001
-        pass
-    state = np.zeros(S)
+    return p, params.solve_params(model, p), paths.sin_path(**kw), np.zeros(params.NUM_STATES[model])
+
+
+def reference_binary_rate(model, T, course_length, n_solves, seconds_budget):
+    """The UNMODIFIED reference node (oracle/_ref/ref_*_time: its translation unit compiled -O2 against stub ROS
+    headers) running its own cycle body -- sampling, predict_States, calc_Weights, determine_OptimalSolution -- on
+    ONE thread, as the node does.  Returns (rollout-steps/s, seconds per solve, K of the bounded sample) or None."""
+    from oracle import ref_runner
+    from ccv_mppi_path_tracker_b200 import params
+    if not ref_runner.timing_available(model):
+        return None
+    p, _, path, state = _cpu_case(model, T, course_length)
+    u0 = np.zeros((T - 1, params.NUM_CONTROLS[model]))
+    k0 = 512
+    t0 = ref_runner.time_solves(model, p, k0, T, state, 0.1, path, u0, 2)[-1]
+    rate = k0 * (T - 1) / max(t0, 1e-6)
+    k_s = int(max(k0, rate * seconds_budget / n_solves / (T - 1)))
+    k_s = max(512, min(1 << 20, (k_s // 512) * 512))
+    ts = ref_runner.time_solves(model, p, k_s, T, state, 0.1, path, u0, n_solves)
+    return k_s, ts
+
+
+def cpu_baseline_run(model, T, course_length, seconds_budget=12.0):
+    """The CPU beside the GPU number: the unmodified reference node on one thread (kind "reference") when
+    oracle/_ref was built, and the FP64 oracle port (OpenMP over samples on all threads, and single-threaded) as
+    additional context.  Bounded samples of the same workload."""
+    import oracle
+    p, sp, path, state = _cpu_case(model, T, course_length)
+    cores = _host_cores()
     # calibrate on a small K, then size the sample for ~seconds_budget
     k0 = 2048
     t0 = oracle.time_solves(model, sp, k0, T, state, 0.1, path, 1, literal_copies=False, nthreads=cores)
@@ -182,42 +207,58 @@ def cpu_baseline_run(model, T, course_length, seconds_budget=12.0):
     # single thread (the reference is single-threaded), smaller sample
     k_1 = max(1024, (k_s // max(cores, 1) // 1024) * 1024)
     t1 = oracle.time_solves(model, sp, k_1, T, state, 0.1, path, 1, literal_copies=False, nthreads=1)
-    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+    port = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"2 chained FP64 oracle solves of K={k_s} (of the workload's K), T={T}, OpenMP over samples on {cores} threads",
             "single_thread_value": k_1 * (T - 1) / t1, "single_thread_sample": f"1 solve of K={k_1}, T={T}, 1 thread"}
+    ref = reference_binary_rate(model, T, course_length, 3, seconds_budget)
+    if ref is None:
+        return port
+    k_r, ts = ref
+    return {"value": k_r * (T - 1) / float(np.mean(ts[1:])), "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"2 timed cycles (after 1 warm-up) of the unmodified reference node (oracle/_ref, -O2, its own "
+                      f"mt19937 sampling included), K={k_r} samples of the workload's K, T={T}, 1 thread (the node is "
+                      f"single-threaded)",
+            "port_all_threads_value": port["value"], "port_all_threads_cores": cores, "port_all_threads_sample": port["sample"],
+            "port_single_thread_value": port["single_thread_value"]}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the ROS nodes themselves cannot be built into
-    a timed binary here) on all host cores, each step a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the solve on the host.  When oracle/_ref holds the
+    compiled reference node (built in the container where /root/reference is mounted; the binaries travel to the GPU
+    box) that is what runs -- single-threaded, like the node; otherwise the FP64 oracle port on all host threads.
+    Each step is one solve of a bounded sample of the workload's K."""
     if rank != 0:
         return
     import oracle
-    from ccv_mppi_path_tracker_b200 import params, paths
     model, K, T, R, L = WORKLOADS[args.workload]
-    p = params.node_params(model, launch=True, horizon=T, **({"roll_off": False} if model == "full_body" else {}))
-    sp = params.solve_params(model, p)
-    kw = dict(params.LAUNCH_PATH[model])
-    kw["course_length"] = L
-    path = paths.sin_path(**kw)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    state = np.zeros(params.NUM_STATES[model])
-    k0 = 2048
-    t0 = oracle.time_solves(model, sp, k0, T, state, 0.1, path, 1, False, cores)
-    rate = k0 * (T - 1) / max(t0, 1e-6)
+    cores = _host_cores()
     total = args.steps + args.warmup
-    k_s = int(min(K * R, max(1024, rate * (90.0 / total) / (T - 1))))
-    k_s = max(1024, (k_s // 1024) * 1024)
-    for _ in range(args.warmup):
-        oracle.time_solves(model, sp, k_s, T, state, 0.1, path, 1, False, cores)
-    t = oracle.time_solves(model, sp, k_s, T, state, 0.1, path, args.steps, False, cores)
+    ref = reference_binary_rate(model, T, L, total, 60.0)
+    if ref is not None:
+        k_s, ts = ref
+        t = float(np.sum(ts[args.warmup:]))
+        kind, used = "reference", 1
+        sample = (f"each step = one cycle of the unmodified reference node (oracle/_ref, -O2) on K={k_s} samples "
+                  f"(bounded sample of K={K * R}), T={T}, 1 thread (the node is single-threaded)")
+    else:
+        p, sp, path, state = _cpu_case(model, T, L)
+        k0 = 2048
+        t0 = oracle.time_solves(model, sp, k0, T, state, 0.1, path, 1, False, cores)
+        rate = k0 * (T - 1) / max(t0, 1e-6)
+        k_s = int(min(K * R, max(1024, rate * (90.0 / total) / (T - 1))))
+        k_s = max(1024, (k_s // 1024) * 1024)
+        for _ in range(args.warmup):
+            oracle.time_solves(model, sp, k_s, T, state, 0.1, path, 1, False, cores)
+        t = oracle.time_solves(model, sp, k_s, T, state, 0.1, path, args.steps, False, cores)
+        kind, used = "port", cores
+        sample = f"each step = one FP64 solve of K={k_s} samples (bounded sample of K={K * R}), T={T}, {cores} OpenMP threads"
     val = args.steps * k_s * (T - 1) / t
-    sample = f"each step = one FP64 solve of K={k_s} samples (bounded sample of K={K * R}), T={T}, {cores} OpenMP threads"
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": args.workload, "model": model, "K_sample": k_s, "T": T},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": kind, "sample": sample,
+                            "host_cores": cores},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

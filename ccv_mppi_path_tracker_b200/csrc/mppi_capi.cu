@@ -10,6 +10,7 @@
 
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mppi_b200.h"
@@ -135,8 +136,13 @@ int fail(mppi_handle h, int code, const std::string &msg) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// u_min <= u_max: the clamp of the FP32 contract is min(max(v, lo), hi) (mppi_math.h), which equals the reference's
+// `if (v < lo) v = lo; else if (v > hi) v = hi;` (DD:62-67) only for ordered bounds
 bool params_valid(const mppi_params *p) {
-  return p && p->lambda > 0.0 && p->resolution > 0.0 && p->control_noise >= 0.0;
+  if (!(p && p->lambda > 0.0 && p->resolution > 0.0 && p->control_noise >= 0.0)) return false;
+  for (int u = 0; u < kMaxControls; ++u)
+    if (!(p->u_min[u] <= p->u_max[u])) return false;
+  return true;
 }
 
 void invalidate_graphs(mppi_handle h) {
@@ -357,7 +363,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   if (!out) return fail(nullptr, MPPI_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (model < 0 || model > 2) return fail(nullptr, MPPI_ERR_INVALID, "unknown model");
-  if (!params_valid(params)) return fail(nullptr, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0");
+  if (!params_valid(params)) return fail(nullptr, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0, u_min <= u_max");
   if (num_samples < 1 || horizon < 2 || horizon > 4096 || n_robots < 1 || n_robots > 65535)
     return fail(nullptr, MPPI_ERR_INVALID, "need num_samples >= 1, 2 <= horizon <= 4096, 1 <= n_robots <= 65535");
   int ndev = 0;
@@ -510,7 +516,7 @@ int mppi_destroy(mppi_handle h) {
 
 int mppi_set_params(mppi_handle h, const mppi_params *params) {
   if (!h) return MPPI_ERR_INVALID;
-  if (!params_valid(params)) return fail(h, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0");
+  if (!params_valid(params)) return fail(h, MPPI_ERR_INVALID, "params: need lambda > 0, resolution > 0, control_noise >= 0, u_min <= u_max");
   h->params = *params;
   return MPPI_OK;
 }

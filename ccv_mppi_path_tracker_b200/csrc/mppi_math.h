@@ -157,15 +157,16 @@ MPPI_HD void sincos_f32(float a, float &s, float &c) {
 }
 
 // sin and cos of a per-step angle INCREMENT (w*dt, roll_v*dt, pitch_v*dt).  For |a| <= 0.35 rad a degree-5 / degree-6
-// minimax pair (|sin error| < 1.4e-8 relative, |cos error| < 1.1e-10, both below half an FP32 ulp); beyond that
+// minimax pair fitted on that interval (|sin error| < 1.5e-8 relative, |cos error| < 1.2e-10, both below half an
+// FP32 ulp); beyond that
 // sincos_f32.  Part of the FP32 contract (host twin and device take the same branch on the same bits).
 constexpr float kSmallIncrement = 0.35f;
 template <bool SMALL = false>
 MPPI_HD void sincos_increment(float a, float &s, float &c) {
   if (SMALL || fabsf(a) <= kSmallIncrement) {
     float z = a * a;
-    s = fmaf(fmaf(z, 8.316085115305715e-3f, -1.6666633325849287e-1f), z * a, a);
-    c = fmaf(fmaf(fmaf(z, -1.3864750323901004e-3f, 4.166661078295986e-2f), z, -0.5f), z, 1.0f);
+    s = fmaf(fmaf(z, 8.299172942064573e-3f, -1.6666535808051738e-1f), z * a, a);
+    c = fmaf(fmaf(fmaf(z, -1.3841075014937032e-3f, 4.166644728107707e-2f), z, -0.5f), z, 1.0f);
   } else {
     sincos_f32(a, s, c);
   }
@@ -278,12 +279,20 @@ struct Attitude {
 // Heading = yaw (DD) or yaw + steer/direction (SD:122, FB:447): cos/sin(yaw + d) by the addition theorem from
 // the carried (cos yaw, sin yaw) and (sd, cd) = sincos_f32(d), which the caller shares with the ZMP model
 // (FB:473-474); (sd, cd) is ignored for DD.
-template <int MODEL, bool SMALL = false>
-MPPI_HD void step_state(float &x, float &y, Attitude<MODEL> &a, const float *u, float dt, float sd, float cd) {
-  float ch = a.cy, sh = a.sy;
+// The three pieces are separate so that a kernel can evaluate the position update with packed instructions
+// (same IEEE operations per element).
+template <int MODEL>
+MPPI_HD void step_heading(const Attitude<MODEL> &a, float sd, float cd, float &ch, float &sh) {
+  ch = a.cy;
+  sh = a.sy;
   if (MODEL != kDiffDrive) rotate(ch, sh, cd, sd);
-  x = fmaf(u[0] * ch, dt, x);
-  y = fmaf(u[0] * sh, dt, y);
+}
+MPPI_HD void step_position(float &x, float &y, float v, float ch, float sh, float dt) {
+  x = fmaf(v * ch, dt, x);
+  y = fmaf(v * sh, dt, y);
+}
+template <int MODEL, bool SMALL = false>
+MPPI_HD void step_attitude(Attitude<MODEL> &a, const float *u, float dt) {
   a.yaw = fmaf(u[1], dt, a.yaw);
   rotate_by<SMALL>(a.cy, a.sy, u[1] * dt);
   if (MODEL == kFullBody) {
@@ -292,6 +301,13 @@ MPPI_HD void step_state(float &x, float &y, Attitude<MODEL> &a, const float *u, 
     rotate_by<SMALL>(a.cr, a.sr, u[3] * dt);
     rotate_by<SMALL>(a.cp, a.sp, u[4] * dt);
   }
+}
+template <int MODEL, bool SMALL = false>
+MPPI_HD void step_state(float &x, float &y, Attitude<MODEL> &a, const float *u, float dt, float sd, float cd) {
+  float ch, sh;
+  step_heading<MODEL>(a, sd, cd, ch, sh);
+  step_position(x, y, u[0], ch, sh, dt);
+  step_attitude<MODEL, SMALL>(a, u, dt);
 }
 
 // zmp_y of FB:468-486 + FB:597-603 for one (sample, t):

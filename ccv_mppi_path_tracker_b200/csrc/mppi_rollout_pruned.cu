@@ -52,6 +52,16 @@ __device__ __forceinline__ u64 dist2_pair(u64 xx, u64 yy, u64 xr, u64 yr) {
   asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(d) : "l"(dy), "l"(m));
   return d;
 }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ float min3f(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -122,6 +132,14 @@ __device__ __forceinline__ int clamp0(int v, int hi) {
 __device__ __forceinline__ uint32_t grid_cell(const GridView &g, float x, float y) {
   const int ix = clamp0(__float2int_rd(fmaf(x, g.inv_h, g.cx)), g.ixmax);
   const int iy = clamp0(__float2int_rd(fmaf(y, g.inv_h, g.cy)), g.iymax);
+  return __ldg(g.cells + (iy * g.nx2 + ix));
+}
+// the same lookup for the packed position {x, y}: one FFMA2 for both axes (same roundings per element)
+__device__ __forceinline__ uint32_t grid_cell(const GridView &g, u64 xy) {
+  float fx, fy;
+  unpack2(fma2(xy, pack2(g.inv_h, g.inv_h), pack2(g.cx, g.cy)), fx, fy);
+  const int ix = clamp0(__float2int_rd(fx), g.ixmax);
+  const int iy = clamp0(__float2int_rd(fy), g.iymax);
   return __ldg(g.cells + (iy * g.nx2 + ix));
 }
 // Exact min_j min(d2(p, r_j), 1e4) over the whole window, given the cell entry of (x, y).
@@ -311,7 +329,7 @@ struct Rollout {
   const SolveParams &sP;
   const GridView &gv;
   const unsigned pairs_s, nom_s;
-  float x, y;
+  u64 xy;  // position {x, y} as one f32x2 register pair
   Attitude<MODEL> att;  // cos / sin of yaw (roll, pitch) carried through the horizon (mppi_math.h)
   CostAcc acc;
   uint32_t cell;
@@ -321,8 +339,7 @@ struct Rollout {
 
   __device__ __forceinline__ Rollout(const ThreadCtx &cx)
       : sP(*cx.sP), gv(cx.gv), pairs_s(cx.pairs_s), nom_s(cx.nom_s) {
-    x = cx.st[0];
-    y = cx.st[1];
+    xy = pack2(cx.st[0], cx.st[1]);
     att.init(cx.st);
     sigma = sP.sigma;
     dt = sP.dt;
@@ -333,27 +350,39 @@ struct Rollout {
       lo[u] = sP.u_min[u];
       hi[u] = sP.u_max[u];
     }
-    cell = grid_cell(gv, x, y);
+    cell = grid_cell(gv, xy);
   }
   // sampling (D5) of step t: normals at shared address src + u * row_bytes; past the last step the result is never
   // used (s_nom is padded)
   __device__ __forceinline__ void make(int t, unsigned src, unsigned row_bytes, float *dst) const {
     const unsigned nom = nom_s + (unsigned)(t * U) * 4u;
+    // mean + sigma * eps (D5) two controls at a time (FFMA2: the same fmaf per element), then the clamp
+    float raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      dst[u] = sample_control(lds32_volatile(src + u * row_bytes), sigma, lds32(nom + u * 4u), lo[u], hi[u]);
+    for (int u = 0; u + 1 < U; u += 2) {
+      const u64 e = pack2(lds32_volatile(src + u * row_bytes), lds32_volatile(src + (u + 1) * row_bytes));
+      const u64 m = pack2(lds32(nom + u * 4u), lds32(nom + (u + 1) * 4u));
+      unpack2(fma2(e, pack2(sigma, sigma), m), raw[u], raw[u + 1]);
+    }
+    if (U & 1) raw[U - 1] = fmaf(lds32_volatile(src + (U - 1) * row_bytes), sigma, lds32(nom + (U - 1) * 4u));
+#pragma unroll
+    for (int u = 0; u < U; ++u) dst[u] = clamp_ref(raw[u], lo[u], hi[u]);
     if (steer_off) dst[2] = 0.f;  // FB:517
   }
   // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
   // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
   // current state, loaded one iteration earlier).
   __device__ __forceinline__ void advance(const float *cur, const float *nxt) {
-    const float x0 = x, y0 = y;
+    float x0, y0;
+    unpack2(xy, x0, y0);
     const float sr0 = att.sr, cr0 = att.cr, sp0 = att.sp, cp0 = att.cp;
-    float sd = 0.f, cd = 1.f;
+    float sd = 0.f, cd = 1.f, ch, sh;
     if (MODEL != kDiffDrive) sincos_f32<SMALL>(cur[2], sd, cd);
-    step_state<MODEL, SMALL>(x, y, att, cur, dt, sd, cd);
-    const uint32_t cell_next = grid_cell(gv, x, y);
+    // step_state (mppi_math.h) with the position update packed: {x, y} = fma({v*ch, v*sh}, dt, {x, y})
+    step_heading<MODEL>(att, sd, cd, ch, sh);
+    xy = fma2(mul2(pack2(cur[0], cur[0]), pack2(ch, sh)), pack2(dt, dt), xy);
+    step_attitude<MODEL, SMALL>(att, cur, dt);
+    const uint32_t cell_next = grid_cell(gv, xy);
     acc.path += min_dist2_cell(cell, pairs_s, x0, y0);
     cell = cell_next;
     const float dv = cur[0] - v_ref;
@@ -368,7 +397,11 @@ struct Rollout {
     }
   }
   __device__ __forceinline__ float finish(const float *st) {
-    if (MODEL != kFullBody) acc.path += min_dist2_cell(cell, pairs_s, x, y);  // state T-1: path term only (D1)
+    if (MODEL != kFullBody) {  // state T-1: path term only (D1)
+      float x, y;
+      unpack2(xy, x, y);
+      acc.path += min_dist2_cell(cell, pairs_s, x, y);
+    }
     float yaw0_err = 0.f;
     if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
       const float4 w01 = lds128(pairs_s);

@@ -48,7 +48,7 @@ typedef struct {
   double v_ref;         /* DD:28 */
   double resolution;    /* path resolution used by calc_RefPath (DD:29, DD:160) */
   double u_min[5];      /* v_min, w_min, steer_min, roll_v_min, pitch_v_min (DD:24-26, SD:26-28, FB:20-26) */
-  double u_max[5];      /* v_max, w_max, steer_max, roll_v_max, pitch_v_max */
+  double u_max[5];      /* v_max, w_max, steer_max, roll_v_max, pitch_v_max; u_min[k] <= u_max[k] is required */
   double path_weight;   /* DD:33 */
   double v_weight;      /* DD:34 (read from "control_weight"), FB:35 */
   double zmp_weight;    /* FB:36; caller applies roll_off (FB:43-46) */

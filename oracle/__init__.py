@@ -74,6 +74,12 @@ def _load_twin():
         lib.twin_atan2.argtypes = [_P(C.c_float), _P(C.c_float), C.c_int, _P(C.c_float)]
         lib.twin_sincos.restype = None
         lib.twin_sincos.argtypes = [_P(C.c_float), C.c_int, _P(C.c_float), _P(C.c_float)]
+        lib.twin_sincos_increment.restype = None
+        lib.twin_sincos_increment.argtypes = [_P(C.c_float), C.c_int, _P(C.c_float), _P(C.c_float)]
+        lib.twin_heading.restype = None
+        lib.twin_heading.argtypes = [C.c_float, _P(C.c_float), C.c_int, _P(C.c_float), _P(C.c_float), _P(C.c_float)]
+        lib.twin_clamp.restype = None
+        lib.twin_clamp.argtypes = [_P(C.c_float), C.c_int, C.c_float, C.c_float, _P(C.c_float)]
         _twin = lib
     return _twin
 
@@ -216,4 +222,30 @@ def twin_atan2(y, x):
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.zeros_like(y)
     lib.twin_atan2(_f(y), _f(x), y.size, _f(out))
+    return out
+
+
+def twin_sincos_increment(a):
+    lib = _load_twin()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    s = np.zeros_like(a)
+    c = np.zeros_like(a)
+    lib.twin_sincos_increment(_f(a), a.size, _f(s), _f(c))
+    return s, c
+
+
+def twin_heading(angle0, increments):
+    """(cos, sin) carried by the contract's rotation recurrence, and the plainly accumulated FP32 angle."""
+    lib = _load_twin()
+    inc = np.ascontiguousarray(increments, dtype=np.float32)
+    c, s, a = (np.zeros_like(inc) for _ in range(3))
+    lib.twin_heading(float(angle0), _f(inc), inc.size, _f(c), _f(s), _f(a))
+    return c, s, a
+
+
+def twin_clamp(v, lo, hi):
+    lib = _load_twin()
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    out = np.zeros_like(v)
+    lib.twin_clamp(_f(v), v.size, float(lo), float(hi), _f(out))
     return out

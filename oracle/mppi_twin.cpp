@@ -105,4 +105,27 @@ void twin_sincos(const float *a, int n, float *s, float *c) {
   for (int i = 0; i < n; ++i) sincos_f32(a[i], s[i], c[i]);
 }
 
+// sin / cos of a per-step angle increment (short polynomial inside +-0.35 rad, sincos_f32 beyond)
+void twin_sincos_increment(const float *a, int n, float *s, float *c) {
+  for (int i = 0; i < n; ++i) sincos_increment(a[i], s[i], c[i]);
+}
+
+// the heading recurrence: (cos, sin) of angle0 advanced by n increments; also the directly accumulated angle
+void twin_heading(float angle0, const float *increments, int n, float *c_out, float *s_out, float *angle_out) {
+  float s, c, a = angle0;
+  sincos_f32(a, s, c);
+  for (int i = 0; i < n; ++i) {
+    rotate_by(c, s, increments[i]);
+    a += increments[i];
+    c_out[i] = c;
+    s_out[i] = s;
+    angle_out[i] = a;
+  }
+}
+
+// clamp of the contract: min.NaN(max.NaN(v, lo), hi) with the PTX ordering of signed zeros
+void twin_clamp(const float *v, int n, float lo, float hi, float *out) {
+  for (int i = 0; i < n; ++i) out[i] = clamp_ref(v[i], lo, hi);
+}
+
 }  // extern "C"

@@ -18,9 +18,7 @@ def available():
     return all(os.path.exists(os.path.join(_HERE, "_ref", b)) for b in BIN.values())
 
 
-def run(model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
-    """node_params: the node's ROS parameters by their reference names (ccv_mppi_path_tracker_b200.params.node_params
-    with `lambda_` -> `lambda`); horizon / num_samples are overridden by T / K."""
+def _write_input(fin, model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
     U, S = NUM_CONTROLS[model], NUM_STATES[model]
     p = {("lambda" if k == "lambda_" else k): float(v) for k, v in node_params.items()}
     p["horizon"] = float(T)
@@ -30,18 +28,42 @@ def run(model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
     st[:S] = np.asarray(state, dtype=np.float64).reshape(S)
     eps = np.ascontiguousarray(eps, dtype=np.float32).reshape(T - 1, K, U)
     u0 = np.ascontiguousarray(u_nominal, dtype=np.float64).reshape(T - 1, U)
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<4i", K, T, path_xy.shape[0], len(p)))
+        for k, v in p.items():
+            f.write(k.encode()[:31].ljust(32, b"\0"))
+            f.write(struct.pack("<d", v))
+        f.write(st.tobytes())
+        f.write(struct.pack("<d", float(dt)))
+        f.write(path_xy.tobytes())
+        f.write(u0.tobytes())
+        f.write(eps.tobytes())
+
+
+def timing_available(model=None):
+    names = [BIN[model]] if model else list(BIN.values())
+    return all(os.path.exists(os.path.join(_HERE, "_ref", b + "_time")) for b in names)
+
+
+def time_solves(model, node_params, K, T, state, dt, path_xy, u_nominal, n_solves):
+    """Seconds of each of n_solves consecutive cycles of the UNMODIFIED reference node (its own sampling(),
+    predict_States(), calc_Weights(), determine_OptimalSolution(); -O2 build, one thread like the node)."""
+    U = NUM_CONTROLS[model]
+    with tempfile.TemporaryDirectory() as td:
+        fin = os.path.join(td, "in.bin")
+        _write_input(fin, model, node_params, K, T, state, dt, path_xy, np.zeros((T - 1, K, U), np.float32), u_nominal)
+        r = subprocess.run([os.path.join(_HERE, "_ref", BIN[model] + "_time"), "--time", fin, str(int(n_solves))],
+                           check=True, stderr=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True)
+    return [float(x) for x in r.stdout.split()]
+
+
+def run(model, node_params, K, T, state, dt, path_xy, eps, u_nominal):
+    """node_params: the node's ROS parameters by their reference names (ccv_mppi_path_tracker_b200.params.node_params
+    with `lambda_` -> `lambda`); horizon / num_samples are overridden by T / K."""
+    U, S = NUM_CONTROLS[model], NUM_STATES[model]
     with tempfile.TemporaryDirectory() as td:
         fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
-        with open(fin, "wb") as f:
-            f.write(struct.pack("<4i", K, T, path_xy.shape[0], len(p)))
-            for k, v in p.items():
-                f.write(k.encode()[:31].ljust(32, b"\0"))
-                f.write(struct.pack("<d", v))
-            f.write(st.tobytes())
-            f.write(struct.pack("<d", float(dt)))
-            f.write(path_xy.tobytes())
-            f.write(u0.tobytes())
-            f.write(eps.tobytes())
+        _write_input(fin, model, node_params, K, T, state, dt, path_xy, eps, u_nominal)
         subprocess.run([os.path.join(_HERE, "_ref", BIN[model]), fin, fout], check=True, stderr=subprocess.DEVNULL)
         raw = open(fout, "rb").read()
     off = 0

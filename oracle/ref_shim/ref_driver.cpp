@@ -12,6 +12,10 @@
 // operator new with zeroed padding makes that read return 0.0 deterministically instead of heap garbage.
 //
 // I/O: argv[1] = input file, argv[2] = output file (raw little-endian, layout in oracle/ref_runner.py).
+// Timing mode (bench.py --impl reference / cpu_baseline): `--time <input file> <n_solves>` runs the reference's OWN
+// cycle body -- sampling(); predict_States(); calc_Weights(); determine_OptimalSolution(); (diff_drive_mppi.cpp:
+// 352-358), its own std::mt19937 draw included -- n_solves times on the calling thread (the node is single
+// threaded, diff_drive_mppi.cpp:336-368) and prints the seconds of each solve.  Built with -O2 as *_time.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -131,10 +135,18 @@ static int run_estimator(const char *fin, const char *fout) {
 }
 #endif
 
+#include <chrono>
+
 int main(int argc, char **argv) {
 #if REF_NODE == 3
   if (argc >= 4 && std::string(argv[1]) == "--estimator") return run_estimator(argv[2], argv[3]);
 #endif
+  int time_solves = 0;
+  if (argc >= 4 && std::string(argv[1]) == "--time") {
+    time_solves = atoi(argv[3]);
+    argv[1] = argv[2];
+    if (time_solves < 1) return 1;
+  }
   if (argc < 3) return 1;
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 1;
@@ -162,6 +174,7 @@ int main(int argc, char **argv) {
 
   Node node;  // constructor reads the parameters (incl. horizon, num_samples) from the table
   node.dt_ = dt;
+  const bool timing = time_solves > 0;
   node.path_.poses.resize(n_path);
   for (int k = 0; k < n_path; ++k) {
     node.path_.poses[k].pose.position.x = path[2 * k];
@@ -184,6 +197,20 @@ int main(int argc, char **argv) {
 #endif
   for (int t = 0; t < T - 1; ++t)
     for (int u = 0; u < U; ++u) (*control(opt, u))[t] = u0[(size_t)t * U + u];
+
+  if (timing) {  // the reference's own cycle body, untouched (its own RNG: results are not reproducible)
+    for (int n = 0; n < time_solves; ++n) {
+      const auto t0 = std::chrono::steady_clock::now();
+      node.sampling();
+      node.predict_States();
+      node.calc_Weights();
+      node.determine_OptimalSolution();
+      const auto t1 = std::chrono::steady_clock::now();
+      printf("%.9f\n", std::chrono::duration<double>(t1 - t0).count());
+      fflush(stdout);
+    }
+    return 0;
+  }
 
   // sampling() with the supplied standard normals: same loop order, the reference's clamp()
   const double lo[5] = {node.v_min_, node.w_min_,

@@ -61,6 +61,10 @@ def test_create_rejects_bad_arguments():
     cp.lambda_ = 0.0
     assert lib.mppi_create(C.byref(h), 0, C.byref(cp), 64, 15, 1, 0) == _capi.MPPI_ERR_INVALID       # lambda <= 0
     assert b"lambda" in lib.mppi_last_error(None)
+    cp.lambda_ = 1.0
+    cp.u_min[1], cp.u_max[1] = 2.0, -2.0                                                              # w_min > w_max
+    assert lib.mppi_create(C.byref(h), 0, C.byref(cp), 64, 15, 1, 0) == _capi.MPPI_ERR_INVALID
+    assert b"u_min" in lib.mppi_last_error(None)
     assert lib.mppi_destroy(None) == _capi.MPPI_OK
 
 

@@ -145,3 +145,56 @@ def test_twin_atan2_accuracy():
     ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
     assert np.abs(a - ref).max() < 4e-7
     assert a[100000] == 0.0  # atan2(0, 0) = 0: duplicate window points (DD:175-178)
+
+
+def test_twin_sincos_increment_accuracy():
+    """The per-step angle increments (w*dt, roll_v*dt, pitch_v*dt): short polynomials inside +-0.35 rad, the general
+    sincos beyond; both below one FP32 ulp of error, no jump at the switch-over."""
+    a = np.concatenate([np.linspace(-0.35, 0.35, 400001), np.linspace(-3.0, 3.0, 100001),
+                        np.nextafter(np.float32(0.35), np.float32([0.0, 1.0])), [0.0, -0.0, 1e-20]]).astype(np.float32)
+    s, c = oracle.twin_sincos_increment(a)
+    a64 = a.astype(np.float64)
+    assert np.abs(s - np.sin(a64)).max() < 1.2e-7
+    assert np.abs(c - np.cos(a64)).max() < 1.2e-7
+    small = np.abs(a) <= 0.35
+    assert np.abs(s[small] - np.sin(a64[small])).max() < 4e-8   # |sin| < 0.35: half an ulp is 1.5e-8
+    assert s[-3] == 0.0 and c[-3] == 1.0
+
+
+def test_heading_recurrence_tracks_the_angle():
+    """(cos yaw, sin yaw) carried by rotations (mppi_math.h rotate_by) against FP64 cos/sin of the exactly summed
+    angle: after 400 steps the pair is as accurate as -- for large accumulated yaw more accurate than -- the FP32
+    angle accumulation it replaces."""
+    rng = np.random.default_rng(3)
+    for mean in (0.0, 0.2, -0.19):
+        inc = (mean + 0.05 * rng.standard_normal(400)).astype(np.float32)
+        c, s, a32 = oracle.twin_heading(0.3, inc)
+        exact = np.float64(np.float32(0.3)) + np.cumsum(inc.astype(np.float64))
+        err_pair = np.hypot(c - np.cos(exact), s - np.sin(exact))
+        err_angle = np.abs(a32.astype(np.float64) - exact)
+        assert err_pair.max() < 8e-6
+        assert np.abs(np.hypot(c.astype(np.float64), s.astype(np.float64)) - 1.0).max() < 4e-6
+        if mean != 0.0:
+            assert err_pair[-1] <= err_angle[-1] + 2e-6
+
+
+def test_twin_clamp_matches_the_reference_clamp():
+    """clamp (DD:62-67) as min(max(v, lo), hi) with NaN pass-through: same value as the reference's two tests."""
+    v = np.concatenate([np.linspace(-5, 5, 1001), [np.nan, np.inf, -np.inf, 0.0, -0.0]]).astype(np.float32)
+    for lo, hi in ((-1.2, 2.0), (0.0, 0.0), (-0.5, -0.25)):
+        out = oracle.twin_clamp(v, lo, hi)
+        lo32, hi32 = np.float32(lo), np.float32(hi)
+        ref = np.where(v < lo32, lo32, np.where(v > hi32, hi32, v)).astype(np.float32)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.array_equal(out[ok], ref[ok])   # equal as values (a zero may differ in sign only)
+
+
+@pytest.mark.skipif(not ref_runner.timing_available(), reason="oracle/_ref timing binaries not built (no /root/reference)")
+def test_reference_timing_binary_runs():
+    """bench.py --impl reference: the unmodified node's own cycle body, timed."""
+    from ccv_mppi_path_tracker_b200 import params, paths
+    p = params.node_params("diff_drive", launch=True, horizon=15, num_samples=200)
+    ts = ref_runner.time_solves("diff_drive", p, 200, 15, np.zeros(3), 0.1,
+                                paths.sin_path(**params.LAUNCH_PATH["diff_drive"]), np.zeros((14, 2)), 3)
+    assert len(ts) == 3 and all(t > 0 for t in ts)
