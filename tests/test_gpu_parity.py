@@ -328,6 +328,52 @@ def test_pruned_scan_bit_identical_to_literal_and_twin(model, K, T):
         assert np.array_equal(costs[_capi.SCAN_PRUNED][0].view(np.uint32), tw["cost"].view(np.uint32)), name
 
 
+@pytest.mark.parametrize("model,K,T", [("diff_drive", 1000, 26), ("diff_drive", 4099, 101), ("steering", 333, 50),
+                                       ("full_body", 1030, 27), ("full_body", 520, 100), ("steering", 2048, 24)])
+def test_noise_ring_variants_bit_identical(model, K, T, monkeypatch):
+    """K2 streams the normals either through per-warp TMA tiles (default) or a per-thread cp.async ring: same
+    per-sample cost bits, equal to the FP32 twin -- with partial warps (K not a multiple of 32), odd horizons and
+    horizons whose step count is not a multiple of the 4-step TMA stage."""
+    case = make_case(model, K, T, seed=5)
+    got = {}
+    for ring in ("1", "0"):
+        monkeypatch.setenv("MPPI_K2_RING", ring)
+        with _make_ctl(case) as ctl:
+            ctl.set_noise(case["eps"][None])
+            ctl.optimal_solution[0] = case["u0"]
+            u = ctl.solve(case["state"], case["dt"]).copy()
+            window, _ = ctl.window()
+            got[ring] = (ctl.costs(), u)
+    assert np.array_equal(got["0"][0].view(np.uint32), got["1"][0].view(np.uint32))
+    assert np.array_equal(got["0"][1], got["1"][1])
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"])
+    assert np.array_equal(got["1"][0].view(np.uint32), tw["cost"].view(np.uint32))
+
+
+@pytest.mark.parametrize("model,overrides,dt", [
+    ("diff_drive", dict(w_max=6.0, w_min=-6.0), 0.1),              # |w dt| up to 0.6 > 0.35: general sincos of the increment
+    ("diff_drive", dict(), 0.3),                                   # a slow cycle: dt = 0.3 s, |w dt| up to 0.6
+    ("steering", dict(steer_max=1.2, steer_min=-1.2), 0.1),        # |steer| > 0.78: range-reduced sincos
+    ("full_body", dict(roll_v_max=5.0, roll_v_min=-5.0, steer_max=1.0, steer_min=-1.0), 0.1),
+])
+def test_large_angles_take_the_general_instantiation(model, overrides, dt):
+    """When a control bound times dt leaves the polynomial range, the kernels run the instantiation with the per-step
+    range tests (angles_are_small() false): still bit-identical to the twin, still within tolerance of FP64."""
+    K, T = 2048, 40
+    case = make_case(model, K, T, seed=13, **overrides)
+    with _make_ctl(case) as ctl:
+        ctl.set_noise(case["eps"][None])
+        ctl.optimal_solution[0] = case["u0"]
+        u_gpu = ctl.solve(case["state"], dt).copy()
+        window, _ = ctl.window()
+        cost_gpu = ctl.costs()
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], dt, window, case["eps"], case["u0"])
+    assert np.array_equal(cost_gpu.view(np.uint32), tw["cost"].view(np.uint32))
+    o = oracle.solve(model, case["sp"], K, T, case["state"], dt, case["path"], case["eps"], case["u0"])
+    assert np.all(np.abs(cost_gpu - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+    assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+
+
 def test_pruned_scan_fast_moving_samples():
     """Rollouts that jump several leaves per step (v_max = 30 m/s) defeat the temporal-coherence guess; the bounds
     must catch every such case and fall back."""
