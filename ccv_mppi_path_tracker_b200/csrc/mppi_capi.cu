@@ -406,6 +406,8 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.grid_max_cells = num_samples / 2 < 256 ? 256 : (num_samples / 2 > 65536 ? 65536 : num_samples / 2);
   if (const char *e = getenv("MPPI_GRID_MAX_CELLS")) d.grid_max_cells = atoi(e);  // tuning experiments only
   if (const char *e = getenv("MPPI_GRID_H_MIN")) d.grid_h_min = (float)atof(e);
+  if (const char *e = getenv("MPPI_GRID_MARGIN")) d.grid_margin = (float)atof(e);
+  if (const char *e = getenv("MPPI_K0_LANES")) d.grid_lanes = atoi(e);
   if (d.planes > 65535) {
     delete h;
     return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");

@@ -170,15 +170,26 @@ struct SlotC {
 // ---------------------------------------------------------------------------------------------------------
 // K0: candidate grid (once per robot and solve)
 // ---------------------------------------------------------------------------------------------------------
-// grid = (cell blocks, robots), 128 threads, one thread per cell.  Every CTA re-derives the grid geometry from the
-// window (same arithmetic, same result); CTA 0 publishes it in ghdr[robot] for K2.
+// grid = (cell blocks, robots), 128 threads, LANES adjacent lanes per cell (each takes every LANES-th window point;
+// the partial results are combined by shuffles).  LANES > 1 shortens the serial chain per cell, which is what the
+// latency configurations wait for; many-robot handles, whose grids together are large, use one lane per cell (least
+// total work).  Every CTA re-derives the grid geometry from the window (same arithmetic, same result); CTA 0
+// publishes it in ghdr[robot] for K2.
+// The grid covers the window's bounding box plus a margin for the lateral spread of the rollouts: a quarter of
+// the distance v_ref * dt * (T-1) a sample travels over the horizon (3 m at T = 100, 1.5 m at T = 50 with the launch
+// parameters: measured optima), or margin_abs when that is positive.  Positions outside scan the whole window.
+template <int LANES>
 __global__ void __launch_bounds__(128)
-    candidate_grid_kernel(const float *__restrict__ window, GridHeader *__restrict__ ghdr, uint32_t *__restrict__ cells,
-                          int T, int win_stride, int max_cells, float h_min, float margin) {
+    candidate_grid_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ window,
+                          GridHeader *__restrict__ ghdr, uint32_t *__restrict__ cells, int T, int win_stride,
+                          int max_cells, float h_min, float margin_abs) {
+  constexpr int kCellLanes = LANES;
+  constexpr int kCellsPerBlock = 128 / LANES;
   extern __shared__ __align__(16) float2 s_win[];
-  __shared__ float s_box[4];
   __shared__ GridHeader s_h;
   const int robot = blockIdx.y;
+  float margin = margin_abs;
+  if (!(margin > 0.f)) margin = fminf(fmaxf(0.25f * fabsf(hdr->P.v_ref) * hdr->P.dt * (float)(T - 1), 0.5f), 6.0f);
   const float *g_win = window + (size_t)robot * win_stride;
   for (int j = threadIdx.x; j < T; j += blockDim.x) s_win[j] = make_float2(g_win[2 * j], g_win[2 * j + 1]);
   __syncthreads();
@@ -235,25 +246,40 @@ __global__ void __launch_bounds__(128)
   __syncthreads();
   const GridHeader gh = s_h;
   const int nx2 = gh.nx + 2, ny2 = gh.ny + 2;  // a failed geometry (nx = ny = 0) leaves a 2 x 2 table of border cells
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x % kCellLanes;
+  const int cell = blockIdx.x * kCellsPerBlock + threadIdx.x / kCellLanes;
+  // the kCellLanes lanes of a cell take the same branches below (they are in one warp: shuffles stay converged)
   if (cell >= nx2 * ny2) return;
   const int tx = cell % nx2, ty = cell / nx2;
   if (tx == 0 || ty == 0 || tx == nx2 - 1 || ty == ny2 - 1) {  // border ring: the whole (padded) window
-    cells[(size_t)robot * max_cells + cell] = cell_entry(0, ((T + 1) / 2 + 1) / 2);
+    if (sub == 0) cells[(size_t)robot * max_cells + cell] = cell_entry(0, ((T + 1) / 2 + 1) / 2);
     return;
   }
+  const unsigned quad = (kCellLanes == 32 ? 0xffffffffu : ((1u << kCellLanes) - 1u))
+                        << ((threadIdx.x & 31) / kCellLanes * kCellLanes);
   const int ix = tx - 1, iy = ty - 1;
   const float ccx = gh.x0 + ((float)ix + 0.5f) * gh.h, ccy = gh.y0 + ((float)iy + 0.5f) * gh.h;
   const float r = 0.70710678f * gh.h * kCellInflate + 1.0e-6f * (fabsf(ccx) + fabsf(ccy));
+  // nearest window point to the cell centre: first minimum, as the serial scan (ties -> lowest index)
   float m = INFINITY;
-  int k0 = 0;
-  for (int j = 0; j < T; ++j) {
+  int k0 = 0x7FFFFFFF;
+  for (int j = sub; j < T; j += kCellLanes) {
     const float dj = dist2(ccx, ccy, s_win[j].x, s_win[j].y);
     if (dj < m) {
       m = dj;
       k0 = j;
     }
   }
+#pragma unroll
+  for (int o = 1; o < kCellLanes; o <<= 1) {
+    const float om = __shfl_xor_sync(quad, m, o);
+    const int ok = __shfl_xor_sync(quad, k0, o);
+    if (om < m || (om == m && ok < k0)) {
+      m = om;
+      k0 = ok;
+    }
+  }
+  if (k0 == 0x7FFFFFFF) k0 = 0;  // every distance NaN
   const float reach = sqrtf(m) + 2.f * r;
   const float thr = reach * reach * kCandSlack;
   // Second, sharper filter for the survivors of the circle test: |p - r_j|^2 - |p - r_k0|^2 is affine in p, so if
@@ -266,7 +292,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
   for (int c = 0; c < 4; ++c) dk[c] = dist2(ccx + ((c & 1) ? hs : -hs), ccy + ((c & 2) ? hs : -hs), kx, ky);
   int lo = T, hi = -1;
-  for (int j = 0; j < T; ++j) {
+  for (int j = sub; j < T; j += kCellLanes) {
     const float jx = s_win[j].x, jy = s_win[j].y;
     if (dist2(ccx, ccy, jx, jy) <= thr) {
       float gap = INFINITY, scale = 0.f;
@@ -278,9 +304,14 @@ __global__ void __launch_bounds__(128)
       }
       if (!(gap > 1.0e-5f * scale + 1.0e-30f)) {  // not provably farther than r_k0 everywhere (or NaN): candidate
         lo = min(lo, j);
-        hi = j;
+        hi = max(hi, j);
       }
     }
+  }
+#pragma unroll
+  for (int o = 1; o < kCellLanes; o <<= 1) {
+    lo = min(lo, __shfl_xor_sync(quad, lo, o));
+    hi = max(hi, __shfl_xor_sync(quad, hi, o));
   }
   // pairs of points, two pairs per scan iteration; an empty candidate set can only arise from NaNs: scan everything
   int q0 = 0, n2 = ((T + 1) / 2 + 1) / 2;
@@ -288,18 +319,33 @@ __global__ void __launch_bounds__(128)
     q0 = lo >> 1;
     n2 = ((hi >> 1) - q0 + 2) >> 1;
   }
-  cells[(size_t)robot * max_cells + cell] = cell_entry(q0, n2);
+  if (sub == 0) cells[(size_t)robot * max_cells + cell] = cell_entry(q0, n2);
 }
 
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
-  dim3 grid((d.grid_max_cells + 127) / 128, d.R);
   const size_t smem = sizeof(float2) * (size_t)d.T;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(candidate_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  // lanes per cell: by the total number of cells of the handle (see the kernel's header comment)
+  const long long total = (long long)d.R * d.grid_max_cells;
+  int lanes = total <= 8192 ? 8 : (total <= 131072 ? 4 : 1);
+  if (d.grid_lanes > 0) lanes = d.grid_lanes;
+#define MPPI_LAUNCH_K0(L)                                                                                        \
+  do {                                                                                                           \
+    if (smem > 48 * 1024) {                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(candidate_grid_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                           \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    dim3 grid((d.grid_max_cells + 128 / L - 1) / (128 / L), d.R);                                                \
+    candidate_grid_kernel<L><<<grid, 128, smem, s>>>(d.hdr, d.window, d.grid_hdr, d.grid_cells, d.T, d.win_stride, \
+                                                     d.grid_max_cells, d.grid_h_min, d.grid_margin);             \
+  } while (0)
+  switch (lanes) {
+    case 8: MPPI_LAUNCH_K0(8); break;
+    case 4: MPPI_LAUNCH_K0(4); break;
+    case 2: MPPI_LAUNCH_K0(2); break;
+    default: MPPI_LAUNCH_K0(1); break;
   }
-  candidate_grid_kernel<<<grid, 128, smem, s>>>(d.window, d.grid_hdr, d.grid_cells, d.T, d.win_stride, d.grid_max_cells,
-                                                d.grid_h_min, d.grid_margin);
+#undef MPPI_LAUNCH_K0
   return cudaGetLastError();
 }
 
