@@ -451,15 +451,24 @@ def main():
         achieved = local_steps * fl / t_k2 / 1e12
         # DRAM traffic of one K2 launch from the committed ncu --set full capture of this workload
         # (profiles/r01_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
-        traffic = 838.2e6 if args.workload == "diff_drive_K1M_T100" else None
+        traffic = 837.8e6 if args.workload == "diff_drive_K1M_T100" else None
         roofline = {"bound": "fp32", "kernel": "rollout_cost", "achieved": achieved, "peak": fp32_peak_max,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": traffic,
                     "traffic_note": "bytes per launch (ncu); algorithmic bytes = 4*U per rollout-step = 830.5e6",
                     "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
                     "frac_at_observed_clock": achieved / fp32_peak_obs,
                     "algorithmic_flop_per_rollout_step": fl,
-                    "note": "algorithmic flop = literal T-point scan (6 flop/pair) + dynamics; the exact pruned scan "
-                            "skips pairs, so frac can exceed what the issue rate alone allows",
+                    "note": "algorithmic flop = literal T-point scan (6 flop/pair) + dynamics (SURVEY.md 8d); the exact "
+                            "pruned scan skips ~95 % of the pairs, so frac exceeds 1 -- see `executed` for what the "
+                            "kernel really issues and `hbm_view` for the same kernel against the HBM roofline",
+                    # what the kernel executes, from the committed ncu --set full capture of this workload at steady
+                    # state (profiles/r01_ncu_full.txt): warp instructions per warp-step and issue-slot utilisation
+                    "executed": ({"warp_instructions_per_warp_step": 86.4, "issue_slot_utilisation": 0.733,
+                                  "fp32_pipe_cycles_active": 0.529, "source": "profiles/r01_ncu_full.txt"}
+                                 if args.workload == "diff_drive_K1M_T100" else None),
+                    "hbm_view": {"bound": "hbm", "achieved": 4 * U * local_steps / t_k2 / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": 4 * U * local_steps / t_k2 / 1e9 / hbm_peak,
+                                 "note": "algorithmic 4*U bytes per rollout-step (the normals, read once)"},
                     "kernel_ms": km}
         nbytes = 4 * U * local_steps
         roof_noise = {"bound": "hbm", "kernel": "noise", "achieved": nbytes / (km["noise"] * 1e-3) / 1e9,
