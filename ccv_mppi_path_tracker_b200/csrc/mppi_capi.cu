@@ -408,6 +408,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   if (const char *e = getenv("MPPI_GRID_H_MIN")) d.grid_h_min = (float)atof(e);
   if (const char *e = getenv("MPPI_GRID_MARGIN")) d.grid_margin = (float)atof(e);
   if (const char *e = getenv("MPPI_K0_LANES")) d.grid_lanes = atoi(e);
+  if (const char *e = getenv("MPPI_K4_GROUPS")) d.k4_groups = atoi(e);
   if (d.planes > 65535) {
     delete h;
     return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");

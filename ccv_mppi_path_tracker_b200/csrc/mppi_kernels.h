@@ -81,6 +81,7 @@ struct DeviceState {
   int grid_lanes = 0;         // > 0: lanes per cell of K0 (tuning); else chosen by the handle's total cell count
   // K2 noise ring: 1 = per-warp TMA tiles of the noise tensor (needs eps_map), 0 = per-thread cp.async
   int k2_ring = 1;
+  int k4_groups = 0;  // > 0: plane groups per K4 block (tuning); else by the number of blocks
   bool eps_map_valid = false;
   CUtensorMap eps_map;  // 2-D {Kp, R * planes} f32, box {32, 4 * U}
 };
