@@ -528,7 +528,7 @@ __device__ __forceinline__ float rollout_thread(const ThreadCtx &cx) {
 // One ring PER WARP: a stage is the tile {32 samples of the warp} x {kStageSteps control steps x U planes} of the
 // plane-major noise tensor, fetched by ONE cp.async.bulk.tensor issued by lane 0 and landing as [row][32] floats
 // (128 B rows, conflict-free column reads).  Completion is signalled on the stage's mbarrier (expect-tx bytes);
-// a slot is refilled after __syncwarp() -- every lane has then consumed its column into registers.  Warps never
+// a slot is refilled after __syncwarp(), once every lane has consumed its column in an Euler step.  Warps never
 // wait for each other.  Per control step this costs ~2 issue slots instead of the ~14 of the per-thread LDGSTS
 // ring (address arithmetic, predicates, commit / wait groups).
 constexpr int kStageSteps = 4;
@@ -620,9 +620,7 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
     r.advance(cb, ca);
     r.make(t + 3, base + 3 * kStepBytes, 128u, cb);
     r.advance(ca, cb);
-    // every lane has read its column of this slot: refill it with the tile kStages ahead, then move on
-    __syncwarp();
-    fetch(tile + kStages, slot);
+    const unsigned done = slot;
     if (++slot == kStages) {
       slot = 0;
       parity ^= 1u;
@@ -630,6 +628,11 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
     mbar_wait(tc.bar_s + slot * 8u, parity);
     r.make(t + 4, col + slot * kTileBytes, 128u, ca);
     r.advance(cb, ca);
+    // Refill the finished slot with the tile kStages ahead.  Every value the lanes loaded from it has been consumed
+    // by an Euler step above (cb, its last row, by the advance just before this line), so no shared-memory read of
+    // the slot is outstanding when the bulk copy is issued; __syncwarp() orders the lanes.
+    __syncwarp();
+    fetch(tile + kStages, done);
   }
   {  // at most kStageSteps - 1 iterations, all inside the current tile; ca = step t on entry
     const unsigned base = col + slot * kTileBytes;
