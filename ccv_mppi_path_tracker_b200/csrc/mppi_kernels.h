@@ -76,7 +76,7 @@ struct DeviceState {
   GridHeader *grid_hdr = nullptr;
   uint32_t *grid_cells = nullptr;
   int grid_max_cells = 0;
-  float grid_h_min = 0.08f;   // measured optimum at K = 2^20 (0.04 .. 0.125 tried)
+  float grid_h_min = 0.05f;   // K = 2^20: flat below 0.05 (0.025 .. 0.10 tried); small handles are bound by max_cells
   float grid_margin = 0.f;    // > 0: absolute margin around the window's bounding box; else a quarter of the horizon reach
   int grid_lanes = 0;         // > 0: lanes per cell of K0 (tuning); else chosen by the handle's total cell count
   // K2 noise ring: 1 = per-warp TMA tiles of the noise tensor (needs eps_map), 0 = per-thread cp.async
