@@ -474,9 +474,13 @@ def main():
         roof_noise = {"bound": "hbm", "kernel": "noise", "achieved": nbytes / (km["noise"] * 1e-3) / 1e9,
                       "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (km["noise"] * 1e-3) / 1e9 / hbm_peak,
                       "algorithmic_bytes_per_rollout_step": 4 * U, "peak_source": peak_src}
-        roof_k4 = {"bound": "hbm", "kernel": "weighted_controls",
-                   "achieved": nbytes / (km["weighted_controls"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": nbytes / (km["weighted_controls"] * 1e-3) / 1e9 / hbm_peak}
+        if km["weighted_controls"] > 0:
+            roof_k4 = {"bound": "hbm", "kernel": "weighted_controls",
+                       "achieved": nbytes / (km["weighted_controls"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": nbytes / (km["weighted_controls"] * 1e-3) / 1e9 / hbm_peak}
+        else:
+            roof_k4 = {"kernel": "weighted_controls", "fused": "per-CTA records inside rollout_cost (K2); kernel_ms.weights "
+                                                               "is the rescale of those records"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -97,6 +97,7 @@ struct mppi_handle_s {
   std::vector<double> last_state;  // [R][S] pose of the last staged solve (mppi_get_window)
   double last_dt = 0.0;
   bool external_noise = false;
+  bool weights_valid = false;  // d.weight holds the last solve's weights (false on the fused-controls path)
   int debug_flags = 0, scan_mode = MPPI_SCAN_AUTO;
   uint64_t seed = 0x5EED0000ull;
   int64_t sample_offset = 0, k_global = 0;
@@ -209,6 +210,21 @@ int effective_scan(mppi_handle h, bool *want_nearest, bool *want_states = nullpt
   return scan;
 }
 
+// K2 with the TMA ring also produces the weighted-control records of its CTAs (then K3 + K4 are replaced by the
+// small rescale kernel): the production path, i.e. the pruned scan without debug taps
+bool fused_controls(mppi_handle h, int scan) {
+  return scan == MPPI_SCAN_PRUNED && h->d.fuse_controls && h->d.cta_part && h->d.eps_map_valid && h->d.k2_ring == 1;
+}
+// the finalize / merge kernels see cta_rescale_groups() partials per robot and plane on that path
+DeviceState tail_state(mppi_handle h, bool fused) {
+  DeviceState t = h->d;
+  if (fused) t.nb3 = t.nchunk = cta_rescale_groups((h->d.K + 127) / 128);
+  return t;
+}
+bool fused_tail_for(mppi_handle h, const DeviceState &t) {
+  return h->n_ranks == 1 && (long long)t.planes * t.nchunk <= 4096;
+}
+
 // the kernel sequence of one solve on stream s (also what gets captured into the graph)
 int issue_kernels(mppi_handle h, cudaStream_t s) {
   const DeviceState &d = h->d;
@@ -230,29 +246,37 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
   else CU_TRY(h, launch_noise(d, s));
   ++n;
   if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, s));
+  const bool fused = fused_controls(h, scan);
+  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, fused, s));
   ++n;
-  if (!fused_weights(h)) {
-    CU_TRY(h, launch_weights(d, s));
+  h->weights_valid = !fused;  // the per-sample weights are a debug tap on the fused path (mppi_get_weights)
+  if (fused) {
+    CU_TRY(h, launch_cta_rescale(d, s));
+    ++n;
+  } else {
+    if (!fused_weights(h)) {
+      CU_TRY(h, launch_weights(d, s));
+      ++n;
+    }
+    CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
     ++n;
   }
-  CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
-  ++n;
+  const DeviceState t = tail_state(h, fused);
   if (h->p2p) {
-    CU_TRY(h, launch_finalize_push(d, s));
+    CU_TRY(h, launch_finalize_push(t, s));
     ++n;
-    CU_TRY(h, launch_merge_wait(d, s));
-    ++n;
-    h->launch_count = n;
-    return MPPI_OK;
-  }
-  if (fused_tail(h)) {
-    CU_TRY(h, launch_finalize_merge(d, s));
+    CU_TRY(h, launch_merge_wait(t, s));
     ++n;
     h->launch_count = n;
     return MPPI_OK;
   }
-  CU_TRY(h, launch_finalize(d, s));
+  if (fused_tail_for(h, t)) {
+    CU_TRY(h, launch_finalize_merge(t, s));
+    ++n;
+    h->launch_count = n;
+    return MPPI_OK;
+  }
+  CU_TRY(h, launch_finalize(t, s));
   ++n;
   if (h->n_ranks > 1) {
     int rc = g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s);
@@ -261,7 +285,7 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
                   std::string("ncclAllGather: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "?"));
     ++n;
   }
-  CU_TRY(h, launch_merge(d, s));
+  CU_TRY(h, launch_merge(t, s));
   ++n;
   h->launch_count = n;
   return MPPI_OK;
@@ -465,10 +489,18 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
   CU_NEW(cudaMalloc((void **)&d.cost, sizeof(float) * (size_t)d.R * d.K));
   CU_NEW(cudaMalloc((void **)&d.weight, sizeof(float) * (size_t)d.R * d.K));
+  const int nb3_weights = d.nb3;  // blocks of the stand-alone weight kernel (also the on-demand weights tap)
   if (fused_weights(h)) d.nb3 = d.nchunk;  // the partial (sum w, sum w^2) come from K4's chunks
-  CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * d.nb3 * 2));
+  CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * (nb3_weights > d.nb3 ? nb3_weights : d.nb3) * 2));
   CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.planes * d.nchunk));
   CU_NEW(cudaMalloc((void **)&d.record, sizeof(float) * (size_t)d.R * d.rec_stride));
+  // Weighted controls inside K2 (per-CTA records) instead of K3 + K4: measured -7 % per solve for 1024 robots x
+  // K = 1024 (K4 is far from the HBM roofline on many small tensors), +1.5 % at K = 2^20 (K4 alone runs at the
+  // roofline; the CTAs' end phase costs K2 more than K4 saves) and +30..80 % on the latency configurations (the
+  // pass is serialised inside a few CTAs) -- so: many-robot handles only.
+  d.fuse_controls = n_robots >= 8;
+  if (const char *e = getenv("MPPI_FUSE_CONTROLS")) d.fuse_controls = atoi(e) != 0;  // tuning experiments / tests
+  CU_NEW(cudaMalloc((void **)&d.cta_part, sizeof(float) * (size_t)d.R * ((d.K + 127) / 128) * d.rec_stride));
   CU_NEW(cudaMalloc((void **)&d.cmin, sizeof(unsigned int) * (size_t)d.R));
   CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
@@ -502,7 +534,7 @@ int mppi_destroy(mppi_handle h) {
   DeviceState &d = h->d;
   if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
-  cudaFree(d.record); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
+  cudaFree(d.record); cudaFree(d.cta_part); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
   cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg);
   cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
   cudaFree(h->d_in); cudaFree(h->d_out);
@@ -722,6 +754,12 @@ int mppi_get_weights(mppi_handle h, int robot, float *weights) {
   if (!h) return MPPI_ERR_INVALID;
   if (robot < 0 || robot >= h->R || !weights) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->weights_valid) {  // fused-controls path: exp(-(c - c_min)/lambda) from the resident costs, on demand
+    DeviceState t = h->d;
+    t.nb3 = (h->K + kWeightBlock * 4 - 1) / (kWeightBlock * 4);
+    CU_TRY(h, launch_weights(t, h->stream));
+    h->weights_valid = true;
+  }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   CU_TRY(h, cudaMemcpy(weights, h->d.weight + (size_t)robot * h->K, sizeof(float) * (size_t)h->K, cudaMemcpyDeviceToHost));
   return MPPI_OK;
@@ -859,24 +897,28 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
     cudaEventRecord(ev[1], s);
     if (scan == MPPI_SCAN_PRUNED) launch_candidate_grid(d, s);
     cudaEventRecord(ev[7], s);
-    launch_rollout_cost(d, scan, want_nearest, false, s);
+    const bool fc = fused_controls(h, scan);
+    launch_rollout_cost(d, scan, want_nearest, false, fc, s);
     cudaEventRecord(ev[2], s);
-    if (!fused_weights(h)) launch_weights(d, s);
+    h->weights_valid = !fc;
+    if (fc) launch_cta_rescale(d, s);  // reported in the "weights" slot; "weighted_controls" is then 0
+    else if (!fused_weights(h)) launch_weights(d, s);
     cudaEventRecord(ev[3], s);
-    launch_weighted_controls(d, fused_weights(h), s);
+    if (!fc) launch_weighted_controls(d, fused_weights(h), s);
     cudaEventRecord(ev[4], s);
-    const bool fused = fused_tail(h);
-    if (h->p2p) launch_finalize_push(d, s);
-    else if (fused) launch_finalize_merge(d, s);
-    else launch_finalize(d, s);
+    const DeviceState ts = tail_state(h, fc);
+    const bool fused = fused_tail_for(h, ts);
+    if (h->p2p) launch_finalize_push(ts, s);
+    else if (fused) launch_finalize_merge(ts, s);
+    else launch_finalize(ts, s);
     cudaEventRecord(ev[5], s);
     if (h->p2p) {
-      launch_merge_wait(d, s);
+      launch_merge_wait(ts, s);
     } else if (!fused) {
       if (h->n_ranks > 1 &&
           g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
         rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
-      launch_merge(d, s);
+      launch_merge(ts, s);
     }
     cudaEventRecord(ev[6], s);
     cudaError_t e = cudaStreamSynchronize(s);

@@ -16,19 +16,19 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// block-level min of the per-thread costs, one atomicMin per block
-__device__ __forceinline__ void block_min_to_global(float c, bool valid, unsigned int *cmin_slot, float *s_red) {
+// block-level min of the per-thread costs, one atomicMin per block; returns the block's minimum to every thread
+// (INFINITY when no thread is valid)
+__device__ __forceinline__ float block_min_to_global(float c, bool valid, unsigned int *cmin_slot, float *s_red) {
   float v = valid ? c : INFINITY;
   v = warp_min(v);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) s_red[wid] = v;
   __syncthreads();
-  if (wid == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    float m = lane < nw ? s_red[lane] : INFINITY;
-    m = warp_min(m);
-    if (lane == 0 && m < INFINITY) atomicMin(cmin_slot, float_to_ordered(m));
-  }
+  const int nw = (blockDim.x + 31) >> 5;
+  float m = lane < nw ? s_red[lane] : INFINITY;
+  m = warp_min(m);
+  if (wid == 0 && lane == 0 && m < INFINITY) atomicMin(cmin_slot, float_to_ordered(m));
+  return m;
 }
 
 __device__ __forceinline__ void load_params_to_shared(SolveParams *dst, const SolveHeader *hdr) {

@@ -80,6 +80,8 @@ struct DeviceState {
   float grid_margin = 0.f;    // > 0: absolute margin around the window's bounding box; else a quarter of the horizon reach
   int grid_lanes = 0;         // > 0: lanes per cell of K0 (tuning); else chosen by the handle's total cell count
   // K2 noise ring: 1 = per-warp TMA tiles of the noise tensor (needs eps_map), 0 = per-thread cp.async
+  bool fuse_controls = false;  // K2 (TMA ring) also produces the weighted-control records (many-robot handles); false: K3 + K4
+  float *cta_part = nullptr;  // [R][ceil(K/128)][rec_stride] per-CTA records {m, S, Q, -, N[P]} of the fused K2
   int k2_ring = 1;
   int k4_groups = 0;  // > 0: plane groups per K4 block (tuning); else by the number of blocks
   bool eps_map_valid = false;
@@ -91,6 +93,7 @@ constexpr int kExchangeHeaderBytes = 256;  // flags[2][G] (G <= 32) at the start
 constexpr int kWeightBlock = 256;   // threads of the weight kernel, 4 samples per thread
 constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
 constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
+constexpr int kRescaleMaxCtas = 128;  // CTA records folded by one block of cta_rescale_kernel
 static_assert(sizeof(SolveHeader) <= kHeaderBytes, "SolveHeader must fit its slot");
 
 // K1  Philox4x32-10 + Box-Muller -> eps (float4 stores).  Also resets cmin.
@@ -98,14 +101,18 @@ cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
 // used instead of K1 when the caller supplied the noise tensor (mppi_set_noise)
 cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
-cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, bool write_states,
+cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, bool write_states, bool fused,
                                 cudaStream_t s);
 // K-1 get_CurrentIndex + calc_RefPath on the device, one CTA per robot (many-robot handles; FP64 like the host path)
 cudaError_t launch_window_builder(const DeviceState &d, cudaStream_t s);
 // K0  candidate grid of the pruned scan, once per robot and solve (mppi_rollout_pruned.cu)
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s);
 // K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
-cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s);
+// fused: the CTAs also write their weighted-control records into d.cta_part (TMA ring only); launch_cta_rescale then
+// replaces K3 + K4 and fills wpart / npart with cta_rescale_groups(n_cta) partials per robot and plane
+cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, cudaStream_t s);
+cudaError_t launch_cta_rescale(const DeviceState &d, cudaStream_t s);
+int cta_rescale_groups(int n_cta);
 bool pruned_scan_supported(int T, int planes);
 // tensor map of d.eps for K2's TMA ring (after d.eps, Kp, R, planes, U are final)
 cudaError_t make_eps_tensor_map(DeviceState &d);

@@ -127,14 +127,9 @@ __device__ __forceinline__ int clamp0(int v, int hi) {
   return r;
 }
 
-// Candidate range of the cell that contains (x, y).  Branch-free lookup: the float->int conversion saturates, the
-// clamp sends everything outside the grid to the border ring.
-__device__ __forceinline__ uint32_t grid_cell(const GridView &g, float x, float y) {
-  const int ix = clamp0(__float2int_rd(fmaf(x, g.inv_h, g.cx)), g.ixmax);
-  const int iy = clamp0(__float2int_rd(fmaf(y, g.inv_h, g.cy)), g.iymax);
-  return __ldg(g.cells + (iy * g.nx2 + ix));
-}
-// the same lookup for the packed position {x, y}: one FFMA2 for both axes (same roundings per element)
+// Candidate range of the cell that contains the packed position {x, y}.  Branch-free lookup: one FFMA2 for both axes
+// (the same fmaf per element), the float->int conversion saturates, the clamp sends everything outside the grid to the
+// border ring.
 __device__ __forceinline__ uint32_t grid_cell(const GridView &g, u64 xy) {
   float fx, fy;
   unpack2(fma2(xy, pack2(g.inv_h, g.inv_h), pack2(g.cx, g.cy)), fx, fy);
@@ -658,7 +653,7 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
                                unsigned int *__restrict__ cmin, int K, int Kp, int planes, int win_stride, int T,
                                int max_cells) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ SolveParams sP;
   __shared__ float s_red[32];
   __shared__ GridHeader s_gh;
@@ -704,6 +699,85 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
   block_min_to_global(c, i < K, cmin + robot, s_red);
 }
 
+// ---- fused weighted-control partials of one CTA's 128 samples (replaces K3 + K4 on the production path) -------
+// calc_Weights (DD:216-222) + determine_OptimalSolution (DD:228-236) against the CTA's own minimum m_cta:
+//   w_i = exp(-(c_i - m_cta)/lambda),  S = sum w,  Q = sum w^2,  N[p] = sum_i w_i * clamp(u*_p + sigma*eps[p][i])
+// written as the record {m_cta, S, Q, -, N[planes]}; cta_rescale_kernel brings the records of all CTAs to the
+// robot's global minimum (the same log-sum-exp merge as between GPUs, section 6 of DESIGN.md).  The CTA re-reads
+// its 128 x planes tile of the normals right after streaming it through the TMA ring -- mostly from L2, and in the
+// shadow of the other CTAs' rollouts (K2 uses a quarter of the HBM bandwidth) -- instead of a separate pass of
+// the whole tensor through HBM.  Not inlined (called once per thread, keeps the rollout loop's code compact).
+template <int MODEL>
+__device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float inv_lambda, float c, bool valid,
+                                                   float m_cta, const float *s_nom, const float *eps_robot, int Kp,
+                                                   int planes, float *rec) {
+  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
+  __shared__ __align__(16) float s_w[128];
+  __shared__ float s_sq[2][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  {
+    const float w = valid ? expf(-(c - m_cta) * inv_lambda) : 0.f;
+    s_w[threadIdx.x] = w;
+    const float sw = warp_sum(w), sq = warp_sum(w * w);
+    if (lane == 0) {
+      s_sq[0][wid] = sw;
+      s_sq[1][wid] = sq;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rec[0] = m_cta;
+    rec[1] = (s_sq[0][0] + s_sq[0][1]) + (s_sq[0][2] + s_sq[0][3]);
+    rec[2] = (s_sq[1][0] + s_sq[1][1]) + (s_sq[1][2] + s_sq[1][3]);
+    rec[3] = 0.f;
+  }
+  const float4 wq = *reinterpret_cast<const float4 *>(&s_w[4 * lane]);  // weights of samples 4*lane .. 4*lane+3
+  const int s0 = blockIdx.x * 128 + 4 * lane;                          // first of this lane's four samples
+  const bool in_range = s0 < Kp;                                        // Kp is a multiple of 4
+  const float *e_base = eps_robot + s0;
+  const float sigma = sP.sigma;
+  const bool steer_off = MODEL == kFullBody && sP.steer_off;
+  // a warp takes 4 consecutive planes at a time: 4 independent 16-byte loads per lane, then one transposing butterfly
+  // reduces the 4 partial sums over the 32 lanes (lanes 0, 8, 16, 24 end up with one plane each); fixed order,
+  // deterministic.  (8 planes at a time would cost the kernel 18 more registers and two resident CTAs per SM.)
+  for (int p0 = wid * 4; p0 < planes; p0 += 16) {
+    float4 e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = min(p0 + k, planes - 1);
+      e[k] = in_range ? __ldcs(reinterpret_cast<const float4 *>(e_base + (size_t)p * Kp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = min(p0 + k, planes - 1);
+      const int u = p % U;
+      const float mean = s_nom[p], lo = sP.u_min[u], hi = sP.u_max[u];
+      float a = wq.x * sample_control(e[k].x, sigma, mean, lo, hi);
+      a = fmaf(wq.y, sample_control(e[k].y, sigma, mean, lo, hi), a);
+      a = fmaf(wq.z, sample_control(e[k].z, sigma, mean, lo, hi), a);
+      a = fmaf(wq.w, sample_control(e[k].w, sigma, mean, lo, hi), a);
+      v[k] = (steer_off && u == 2) ? 0.f : a;  // FB:517: every sample of that control is 0
+    }
+    // 4 values x 32 lanes -> lane l (l % 8 == 0) holds plane p0 + (l >> 3 with the two bits swapped: see idx)
+    const bool up = lane & 16;
+    float r[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = up ? v[k] : v[k + 2];
+      const float keep = up ? v[k + 2] : v[k];
+      r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const bool up8 = lane & 8;
+    float r1 = (up8 ? r[1] : r[0]) + __shfl_xor_sync(0xffffffffu, up8 ? r[0] : r[1], 8);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 4);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+    const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // value index held by this lane
+    if ((lane & 7) == 0 && p0 + idx < planes) rec[4 + p0 + idx] = r1;
+  }
+}
+
 // K2 with the TMA ring.  Same prologue as above; dynamic shared memory = ring [4 warps][kStages][rows][32] (1 KB
 // aligned) | window pairs | warm start.  Whole warps run the rollout (the refill needs all 32 lanes at the
 // __syncwarp); lanes past K compute on zero / padding normals and are masked at the store.
@@ -718,7 +792,8 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
                             const float *__restrict__ nominal, const float *__restrict__ window,
                             const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
                             const uint32_t *__restrict__ cells, float *__restrict__ cost,
-                            unsigned int *__restrict__ cmin, int K, int planes, int win_stride, int T, int max_cells) {
+                            unsigned int *__restrict__ cmin, int K, int planes, int win_stride, int T, int max_cells,
+                            const float *__restrict__ eps, int Kp, float *__restrict__ cta_part, int part_stride) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   constexpr int kWarpRingBytes = kStages * kStageSteps * U * 128;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -772,7 +847,54 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
     c = angles_are_small(sP) ? rollout_thread_tma<MODEL, true>(cx, tc) : rollout_thread_tma<MODEL, false>(cx, tc);
     if (i < K) cost[(size_t)robot * K + i] = c;
   }
-  block_min_to_global(c, i < K, cmin + robot, s_red);
+  const float m_cta = block_min_to_global(c, i < K, cmin + robot, s_red);
+  if (cta_part == nullptr) return;  // kernel argument: uniform
+  cta_weighted_controls<MODEL>(sP, hdr->inv_lambda, c, i < K, m_cta, s_nom, eps + (size_t)robot * planes * Kp, Kp, planes,
+                               cta_part + ((size_t)robot * gridDim.x + blockIdx.x) * part_stride);
+}
+
+// K3': brings the per-CTA records of K2 to the robot's global minimum and folds them into the partial arrays the
+// finalize kernels already sum:  a_c = exp(-(m_c - c_min)/lambda);  wpart[g] = {sum_c a_c S_c, sum_c a_c^2 Q_c},
+// npart[p][g] = sum_c a_c N_c[p]  over the CTAs c of group g (fixed order).  grid = (groups, robots).
+__global__ void __launch_bounds__(256)
+    cta_rescale_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
+                       const unsigned int *__restrict__ cmin, float *__restrict__ wpart, float *__restrict__ npart,
+                       int planes, int n_cta, int part_stride, int groups) {
+  __shared__ float s_a[kRescaleMaxCtas];
+  const int robot = blockIdx.y, g = blockIdx.x;
+  const int per = (n_cta + groups - 1) / groups;  // <= kRescaleMaxCtas (launch_cta_rescale)
+  const int c0 = g * per, c1 = min(c0 + per, n_cta);
+  const float c_min = ordered_to_float(cmin[robot]);
+  const float inv_lambda = hdr->inv_lambda;
+  const float *part = cta_part + (size_t)robot * n_cta * part_stride;
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+    s_a[c - c0] = expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda);
+  __syncthreads();
+  for (int p = threadIdx.x; p < planes; p += blockDim.x) {
+    float n = 0.f;
+    for (int c = c0; c < c1; ++c) n = fmaf(s_a[c - c0], part[(size_t)c * part_stride + 4 + p], n);
+    npart[((size_t)robot * planes + p) * groups + g] = n;
+  }
+  if (threadIdx.x == 0) {
+    float S = 0.f, Q = 0.f;
+    for (int c = c0; c < c1; ++c) {
+      const float a = s_a[c - c0];
+      S = fmaf(a, part[(size_t)c * part_stride + 1], S);
+      Q = fmaf(a * a, part[(size_t)c * part_stride + 2], Q);
+    }
+    wpart[((size_t)robot * groups + g) * 2] = S;
+    wpart[((size_t)robot * groups + g) * 2 + 1] = Q;
+  }
+}
+
+int cta_rescale_groups(int n_cta) { return (n_cta + kRescaleMaxCtas - 1) / kRescaleMaxCtas; }
+
+cudaError_t launch_cta_rescale(const DeviceState &d, cudaStream_t s) {
+  const int n_cta = (d.K + 127) / 128;
+  dim3 grid(cta_rescale_groups(n_cta), d.R);
+  cta_rescale_kernel<<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.wpart, d.npart, d.planes, n_cta, d.rec_stride,
+                                          (int)grid.x);
+  return cudaGetLastError();
 }
 
 // Tensor map of the noise tensor for the TMA ring: 2-D {Kp samples, R * planes rows} of f32, box {32, kStageSteps*U}.
@@ -799,7 +921,7 @@ cudaError_t make_eps_tensor_map(DeviceState &d) {
   return cudaSuccess;
 }
 
-cudaError_t launch_rollout_cost_tma(const DeviceState &d, cudaStream_t s) {
+cudaError_t launch_rollout_cost_tma(const DeviceState &d, bool fused, cudaStream_t s) {
   dim3 grid((d.K + 127) / 128, d.R);
   const size_t smem = pruned_tma_smem_bytes(d.T, d.planes, d.U);
 #define MPPI_LAUNCH_TMA(M)                                                                                       \
@@ -811,7 +933,8 @@ cudaError_t launch_rollout_cost_tma(const DeviceState &d, cudaStream_t s) {
     }                                                                                                            \
     rollout_cost_tma_kernel<M><<<grid, 128, smem, s>>>(d.eps_map, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, \
                                                        d.grid_cells, d.cost, d.cmin, d.K, d.planes, d.win_stride, \
-                                                       d.T, d.grid_max_cells);                                   \
+                                                       d.T, d.grid_max_cells, d.eps, d.Kp,                       \
+                                                       fused ? d.cta_part : nullptr, d.rec_stride);              \
   } while (0)
   switch (d.model) {
     case kDiffDrive: MPPI_LAUNCH_TMA(kDiffDrive); break;
@@ -822,8 +945,8 @@ cudaError_t launch_rollout_cost_tma(const DeviceState &d, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_cost_pruned(const DeviceState &d, cudaStream_t s) {
-  if (d.eps_map_valid && d.k2_ring == 1) return launch_rollout_cost_tma(d, s);
+cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, cudaStream_t s) {
+  if (d.eps_map_valid && d.k2_ring == 1) return launch_rollout_cost_tma(d, fused, s);
   dim3 grid((d.K + 127) / 128, d.R);
   const size_t smem = pruned_smem_bytes(d.T, d.planes, d.U);
 #define MPPI_LAUNCH_PRUNED(M)                                                                                    \
