@@ -17,11 +17,18 @@
 //     of magnitude above the FP32 rounding of the distances involved), thinned by a corner test against the point
 //     k0 nearest to c: |p - r_j|^2 - |p - r_k0|^2 is affine in p, positive at the four cell corners => r_j is
 //     strictly farther than r_k0 everywhere in the cell (this keeps far-from-path cells at 3-5 candidates).
-// K2 looks the cell of each predicted state up (one FMA + float->int per axis, one 32-bit load) and evaluates
-// exact squared distances only for that range -- about 4-12 points instead of T, independent of T -- with
+// K2 looks the cell of each predicted state up (one packed FMA + float->int per axis, one 32-bit load) and evaluates
+// exact squared distances only for that range -- about 4-8 points instead of T, independent of T -- with
 // Blackwell's packed FP32 pipe (sub/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2, two window points per instruction,
 // the same IEEE roundings per element as mppi::dist2) and the 3-input FMNMX3.  States outside the grid scan the
 // whole window.  min() is exact and order independent, so the accumulated path cost has the literal scan's bits.
+//
+// Kernels in this file:
+//   candidate_grid_kernel<LANES>     K0
+//   rollout_cost_tma_kernel<MODEL>   K2, production: the normals arrive through a per-warp TMA ring; for many-robot
+//                                    handles the CTA also reduces its weighted controls (cta_weighted_controls)
+//   rollout_cost_pruned_kernel<MODEL> K2 with a per-thread cp.async ring (MPPI_K2_RING=0; same bits)
+//   cta_rescale_kernel               K3': per-CTA records -> partial sums at the robot's global minimum
 #include <cuda.h>
 
 #include "mppi_device.cuh"
