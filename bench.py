@@ -451,7 +451,7 @@ def main():
         achieved = local_steps * fl / t_k2 / 1e12
         # DRAM traffic of one K2 launch from the committed ncu --set full capture of this workload
         # (profiles/r01_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
-        traffic = 837.8e6 if args.workload == "diff_drive_K1M_T100" else None
+        traffic = 838.8e6 if args.workload == "diff_drive_K1M_T100" else None
         roofline = {"bound": "fp32", "kernel": "rollout_cost", "achieved": achieved, "peak": fp32_peak_max,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": traffic,
                     "traffic_note": "bytes per launch (ncu); algorithmic bytes = 4*U per rollout-step = 830.5e6",
@@ -463,8 +463,8 @@ def main():
                             "kernel really issues and `hbm_view` for the same kernel against the HBM roofline",
                     # what the kernel executes, from the committed ncu --set full capture of this workload at steady
                     # state (profiles/r01_ncu_full.txt): warp instructions per warp-step and issue-slot utilisation
-                    "executed": ({"warp_instructions_per_warp_step": 86.4, "issue_slot_utilisation": 0.733,
-                                  "fp32_pipe_cycles_active": 0.529, "source": "profiles/r01_ncu_full.txt"}
+                    "executed": ({"warp_instructions_per_warp_step": 81.9, "issue_slot_utilisation": 0.736,
+                                  "fp32_pipe_cycles_active": 0.501, "source": "profiles/r01_ncu_full.txt"}
                                  if args.workload == "diff_drive_K1M_T100" else None),
                     "hbm_view": {"bound": "hbm", "achieved": 4 * U * local_steps / t_k2 / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": 4 * U * local_steps / t_k2 / 1e9 / hbm_peak,
