@@ -653,3 +653,95 @@ def test_many_handles_create_destroy():
         ref = u if ref is None else ref
         assert np.array_equal(u, ref)
     assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20
+
+
+# ---- BASELINE.json's full sizes, through size-independent properties ---------------------------------------------
+def test_full_size_sharded_config_through_stripes_and_shard_merge():
+    """Config 4 at its full per-GPU size (diff_drive, K = 2^20, T = 100).  The FP64 oracle cannot run 10^8 rollout
+    steps in a test, so the full-size solve is checked through properties that do not depend on K:
+      * a sample's noise and cost are functions of (seed, solve, robot, sample) only -- three 4096-sample stripes of
+        the big solve, recomputed by small shard handles at the same global sample offsets, have identical cost
+        bits, equal to the FP32 twin on the stripes' dumped noise and within tolerance of the FP64 oracle;
+      * c_min, sum w and ESS follow from the 2^20 costs (float64 on the host);
+      * the controls equal the log-sum-exp merge of 8 shard handles of 2^17 samples (what 8 GPUs exchange)."""
+    from ccv_mppi_path_tracker_b200 import merge_partials
+    K, T, S = 1 << 20, 100, 4096
+    case = make_case("diff_drive", S, T, seed=4)
+    big = make_case("diff_drive", K, T, seed=4)
+    with _make_ctl(big) as ctl:
+        ctl.set_seed(0x5EED0004, 2)
+        u_big = ctl.solve(case["state"], case["dt"]).copy()
+        cost_big, st_big = ctl.costs(), ctl.stats()
+        window, _ = ctl.window()
+    assert np.isfinite(cost_big).all()
+    w64 = np.exp(-(cost_big.astype(np.float64) - cost_big.min()) / case["sp"]["lambda_"])
+    assert st_big["c_min"] == float(cost_big.min())
+    assert abs(st_big["sum_w"] - w64.sum()) <= 1e-5 * w64.sum()
+    assert abs(st_big["ess"] - w64.sum() ** 2 / (w64 ** 2).sum()) <= 1e-3 * st_big["ess"]
+    u0 = np.zeros((T - 1, 2))
+    for off in (0, 517 * 1024, K - S):
+        with _make_ctl(case) as sh:
+            sh.set_seed(0x5EED0004, 2)
+            sh.set_shard(off, K, 0)
+            sh.solve(case["state"], case["dt"])
+            c_s, eps_s = sh.costs(), sh.noise()
+        assert np.array_equal(c_s.view(np.uint32), cost_big[off:off + S].view(np.uint32)), off
+        tw = oracle.twin_rollout_cost("diff_drive", case["sp"], S, T, case["state"], case["dt"], window, eps_s, u0)
+        assert np.array_equal(c_s.view(np.uint32), tw["cost"].view(np.uint32)), off
+        o = oracle.solve("diff_drive", case["sp"], S, T, case["state"], case["dt"], case["path"], eps_s, u0, nthreads=4)
+        assert np.all(np.abs(c_s - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL), off
+    part = make_case("diff_drive", K // 8, T, seed=4)
+    recs = []
+    for g in range(8):
+        with _make_ctl(part) as sh:
+            sh.set_seed(0x5EED0004, 2)
+            sh.set_shard(g * (K // 8), K, 0)
+            sh.solve(case["state"], case["dt"])
+            recs.append(sh.record())
+    u_m, st = merge_partials(np.stack(recs), case["sp"]["lambda_"])
+    assert st["c_min"] == st_big["c_min"]
+    assert (np.abs(u_m.reshape(T - 1, 2) - u_big) / _urange(case)).max() <= 2e-5
+    assert abs(st["ess"] - st_big["ess"]) <= 1e-3 * st_big["ess"]
+
+
+def test_full_size_batched_config_through_single_robot_handles():
+    """Config 5 at its full per-GPU size (1024 robots x K = 1024 x T = 50, windows built on the device): a robot's
+    result depends on its own (path, state, global robot index) only -- a handful of robots, recomputed one by one by
+    single-robot handles placed at the same global robot index, have identical windows and cost bits and (K3 + K4
+    instead of the per-CTA records) the same controls up to FP32 summation order; one robot also goes through the FP64
+    oracle."""
+    R, K, T = 1024, 1024, 50
+    case = make_case("diff_drive", K, T, seed=6)
+    rng = np.random.default_rng(60)
+    variants = []
+    for k in range(8):
+        kw = dict(params.LAUNCH_PATH["diff_drive"])
+        kw["delta1"] = 2 * np.pi * k / 8
+        variants.append(paths.sin_path(**kw))
+    states = np.zeros((R, 3))
+    for r in range(R):
+        p = variants[r % 8]
+        j = r % (p.shape[0] - 1)
+        states[r, :2] = p[j] + 0.1 * rng.standard_normal(2)
+        states[r, 2] = np.arctan2(p[j + 1, 1] - p[j, 1], p[j + 1, 0] - p[j, 0]) + 0.1 * rng.standard_normal()
+    with CONTROLLERS["diff_drive"](launch=True, n_robots=R, horizon=T, num_samples=K) as ctl:
+        for r in range(R):
+            ctl.set_path(variants[r % 8], robot=r)
+        ctl.set_seed(0x5EED0005, 1)
+        u_all = ctl.solve(states, case["dt"]).copy()
+        picks = [0, 1, 511, 777, R - 1]
+        got = {r: (ctl.costs(r), ctl.window(r)[0], ctl.stats(r)) for r in picks}
+    assert np.isfinite(u_all).all()
+    for r in picks:
+        with _make_ctl(case) as one:
+            one.set_path(variants[r % 8])
+            one.set_seed(0x5EED0005, 1)
+            one.set_shard(0, K, r)
+            u_1 = one.solve(states[r], case["dt"]).copy()
+            c_1, w_1, eps_1 = one.costs(), one.window()[0], one.noise()
+        assert np.array_equal(w_1, got[r][1]), r
+        assert np.array_equal(c_1.view(np.uint32), got[r][0].view(np.uint32)), r
+        assert (np.abs(u_1 - u_all[r]) / _urange(case)).max() <= 2e-5, r
+    o = oracle.solve("diff_drive", case["sp"], K, T, states[r], case["dt"], variants[r % 8], eps_1, np.zeros((T - 1, 2)))
+    assert (np.abs(u_all[r] - o["u_new"]) / _urange(case)).max() <= U_TOL
+    assert np.all(np.abs(got[r][0] - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
