@@ -289,6 +289,53 @@ def latency_probe(device, n_solves=1000):
             "what": "host-observed mppi_solve(): host state in -> controls on host, CUDA graph replay"}
 
 
+def sweep_k(device, model="diff_drive", T=100, n_solves=60):
+    """BASELINE.json's metric is quoted "vs K": rollout-steps/s (device-resident, back-to-back enqueues, CUDA events)
+    and host-observed solve latency p50 (mppi_solve() with host buffers; CUDA graph for K <= 2^16) for K = 2^10 .. 2^20,
+    one robot, launch-file parameters.  One GPU; the sharded runs scale the K = 2^20 row (weak scaling)."""
+    import torch
+    from ccv_mppi_path_tracker_b200 import CONTROLLERS, params, paths
+    kw = dict(params.LAUNCH_PATH[model])
+    path = paths.sin_path(**kw)
+    S = params.NUM_STATES[model]
+    rows = []
+    for e in range(10, 21):
+        K = 1 << e
+        ov = {"roll_off": False} if model == "full_body" else {}
+        ctl = CONTROLLERS[model](launch=True, device=device, horizon=T, num_samples=K, **ov)
+        ctl.set_path(path)
+        ctl.set_seed(0x5EED0000 + e, 0)
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        ctl.set_stream(stream.cuda_stream)
+        state = np.zeros(S)
+        ctl.upload(state, 0.1, with_nominal=True)
+        for _ in range(5):
+            ctl.enqueue()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n_solves):
+            ctl.enqueue()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_solves
+        ctl.use_graph(K <= (1 << 16))
+        for _ in range(5):
+            ctl.solve(state, 0.1)
+        ts = np.empty(n_solves)
+        for k in range(n_solves):
+            t0 = time.perf_counter()
+            ctl.solve(state, 0.1)
+            ts[k] = time.perf_counter() - t0
+        rows.append({"K": K, "T": T, "device_ms_per_solve": ms, "rollout_steps_per_sec": K * (T - 1) / (ms * 1e-3),
+                     "solve_p50_us": float(np.percentile(ts, 50) * 1e6), "solve_p99_us": float(np.percentile(ts, 99) * 1e6),
+                     "launches_per_solve": ctl.launch_count()})
+        ctl.close()
+    return {"metric": "rollout_steps_per_sec and solve p50 latency vs K", "model": model, "T": T, "n_gpus": 1,
+            "solves_per_point": n_solves, "data": "synthetic", "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,8 +348,15 @@ def main():
     ap.add_argument("--scan", default="auto", choices=["auto", "literal", "pruned"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="sample-sharded solves: records exchanged by NVLink peer stores inside the finalize kernel, or by ncclAllGather")
+    ap.add_argument("--sweep", action="store_true",
+                    help="instead of the bench line: rollout-steps/s and solve latency p50 vs K = 2^10..2^20 (one GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.sweep:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(sweep_k(0)), flush=True)
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -745,3 +745,21 @@ def test_full_size_batched_config_through_single_robot_handles():
     o = oracle.solve("diff_drive", case["sp"], K, T, states[r], case["dt"], variants[r % 8], eps_1, np.zeros((T - 1, 2)))
     assert (np.abs(u_all[r] - o["u_new"]) / _urange(case)).max() <= U_TOL
     assert np.all(np.abs(got[r][0] - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+
+
+def test_full_size_full_body_config_against_the_oracle():
+    """Config 3 at its full size (full_body, K = 16384, T = 100, every cost term on): small enough for the FP64 oracle
+    itself -- costs bit-exact against the twin, within tolerance of FP64, controls within tolerance."""
+    K, T = 16384, 100
+    case = make_case("full_body", K, T, seed=33)
+    with _make_ctl(case) as ctl:
+        ctl.set_seed(0x5EED0003, 0)
+        ctl.optimal_solution[0] = case["u0"]
+        u_gpu = ctl.solve(case["state"], case["dt"]).copy()
+        eps, cost = ctl.noise(), ctl.costs()
+        window, _ = ctl.window()
+    tw = oracle.twin_rollout_cost("full_body", case["sp"], K, T, case["state"], case["dt"], window, eps, case["u0"])
+    assert np.array_equal(cost.view(np.uint32), tw["cost"].view(np.uint32))
+    o = oracle.solve("full_body", case["sp"], K, T, case["state"], case["dt"], case["path"], eps, case["u0"], nthreads=8)
+    assert np.all(np.abs(cost - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+    assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
