@@ -506,23 +506,24 @@ def main():
         # DRAM traffic of one K2 launch from the committed ncu --set full capture of this workload
         # (profiles/r01_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
         traffic = 838.8e6 if args.workload == "diff_drive_K1M_T100" else None
-        roofline = {"bound": "fp32", "kernel": "rollout_cost", "achieved": achieved, "peak": fp32_peak_max,
-                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_max, "traffic": traffic,
-                    "traffic_note": "bytes per launch (ncu); algorithmic bytes = 4*U per rollout-step = 830.5e6",
-                    "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
-                    "frac_at_observed_clock": achieved / fp32_peak_obs,
-                    "algorithmic_flop_per_rollout_step": fl,
-                    "note": "algorithmic flop = literal T-point scan (6 flop/pair) + dynamics (SURVEY.md 8d); the exact "
-                            "pruned scan skips ~95 % of the pairs, so frac exceeds 1 -- see `executed` for what the "
-                            "kernel really issues and `hbm_view` for the same kernel against the HBM roofline",
-                    # what the kernel executes, from the committed ncu --set full capture of this workload at steady
-                    # state (profiles/r01_ncu_full.txt): warp instructions per warp-step and issue-slot utilisation
+        k2_bytes = 4 * U * local_steps  # algorithmic: the normals, read once (4*U B per rollout-step)
+        roofline = {"bound": "hbm", "kernel": "rollout_cost", "achieved": k2_bytes / t_k2 / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": k2_bytes / t_k2 / 1e9 / hbm_peak, "traffic": traffic,
+                    "traffic_note": "dram bytes per launch (ncu --set full, profiles/r01_ncu_full.txt); algorithmic "
+                                    "bytes = 4*U per rollout-step",
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                    "note": "the dominant kernel is FP32/ALU-issue bound, not HBM bound (DESIGN.md section 4): `fp32_view` "
+                            "is SURVEY.md 8d's roofline for it, `executed` what it really issues",
+                    # algorithmic flop of the LITERAL T-point scan (6 flop/pair) + dynamics against the FP32
+                    # peak; the exact pruned scan skips ~95 % of the pairs, so this fraction exceeds 1
+                    "fp32_view": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_max, "unit": "TFLOP/s",
+                                  "frac": achieved / fp32_peak_max, "frac_at_observed_clock": achieved / fp32_peak_obs,
+                                  "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src})",
+                                  "algorithmic_flop_per_rollout_step": fl},
+                    # from the committed ncu --set full capture of this workload at steady state
                     "executed": ({"warp_instructions_per_warp_step": 81.9, "issue_slot_utilisation": 0.736,
                                   "fp32_pipe_cycles_active": 0.501, "source": "profiles/r01_ncu_full.txt"}
                                  if args.workload == "diff_drive_K1M_T100" else None),
-                    "hbm_view": {"bound": "hbm", "achieved": 4 * U * local_steps / t_k2 / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "frac": 4 * U * local_steps / t_k2 / 1e9 / hbm_peak,
-                                 "note": "algorithmic 4*U bytes per rollout-step (the normals, read once)"},
                     "kernel_ms": km}
         nbytes = 4 * U * local_steps
         roof_noise = {"bound": "hbm", "kernel": "noise", "achieved": nbytes / (km["noise"] * 1e-3) / 1e9,
