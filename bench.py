@@ -472,6 +472,11 @@ def main():
     value = steps_per_solve * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through mppi_solve(): host buffers in, host buffers out, every step ---------------------
+    # (unsharded handles replay the solve -- H2D copy, kernels, D2H copy -- as one CUDA graph: mppi_use_graph, the
+    # same public switch the latency path uses; MPPI_BENCH_NO_GRAPH=1 times the plain stream launches instead)
+    e2e_graph = world == 1 and not os.environ.get("MPPI_BENCH_NO_GRAPH")
+    if e2e_graph:
+        ctl.use_graph(True)
     for _ in range(min(args.warmup, 3)):
         ctl.solve(states, 0.1)
     sync_all()
@@ -486,7 +491,9 @@ def main():
         e2e_s = float(t.item())
     h2d, d2h = ctl.io_bytes()
     e2e = {"value": steps_per_solve * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps}
+           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "cuda_graph": bool(e2e_graph)}
+    if e2e_graph:
+        ctl.use_graph(False)
 
     # ---- per-kernel device time (CUDA events between the launches, on the launching stream) -----------------
     km = ctl.time_kernels(max(3, min(args.steps, 10)))
