@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include <new>
 #include <string>
 #include <utility>
@@ -301,7 +302,11 @@ int wait_staging_free(mppi_handle h) {
 
 // host part of the cycle: windows (double), header, robot-centred FP32 inputs into the pinned block
 int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_nominal) {
-  if (!state || !(dt > 0.0)) return fail(h, MPPI_ERR_INVALID, "state must be non-NULL and dt > 0");
+  if (!state || !(dt > 0.0) || !std::isfinite(dt)) return fail(h, MPPI_ERR_INVALID, "state must be non-NULL and dt > 0");
+  // The reference lets a NaN pose run through the cycle and publishes NaN commands (DD:117 -> DD:250); here it is an
+  // error the caller can see: the kernels' grid lookup and min() do not propagate NaN the way the FP64 loops do.
+  for (size_t k = 0; k < (size_t)h->R * h->S; ++k)
+    if (!std::isfinite(state[k])) return fail(h, MPPI_ERR_INVALID, "state must be finite");
   int rc = wait_staging_free(h);
   if (rc) return rc;
   fill_header(h, dt);

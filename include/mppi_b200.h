@@ -133,7 +133,8 @@ int mppi_set_noise(mppi_handle h, const float *eps);
  *   dt         dt_ of this cycle (DD:347)
  *   u_nominal  n_robots x (T-1) x U doubles, in: optimal_solution of the previous cycle (warm start, DD:89-90),
  *              out: the new optimal_solution (DD:230-235 with the t<T-1 bound)
- * Host buffers in, host buffers out; synchronous (returns after u_nominal is written). */
+ * Host buffers in, host buffers out; synchronous (returns after u_nominal is written).
+ * MPPI_ERR_INVALID for dt <= 0 or a non-finite state (the reference would publish NaN commands, DD:117 -> DD:250). */
 int mppi_solve(mppi_handle h, const double *state, double dt, double *u_nominal);
 
 /* The same cycle split for pipelining and for device-resident timing:

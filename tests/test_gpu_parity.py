@@ -269,6 +269,19 @@ def test_roll_off_and_steer_off_switches():
             assert np.all(u_gpu[:, 2] == 0.0)
 
 
+def test_non_finite_state_is_an_error():
+    case = make_case("diff_drive", 256, 15)
+    with _make_ctl(case) as ctl:
+        for bad in (np.nan, np.inf):
+            st = case["state"].copy()
+            st[1] = bad
+            with pytest.raises(_capi.MppiError) as e:
+                ctl.solve(st, case["dt"])
+            assert e.value.code == _capi.MPPI_ERR_INVALID and "finite" in str(e.value)
+        u = ctl.solve(case["state"], case["dt"])  # the handle stays usable
+        assert np.isfinite(u).all()
+
+
 def test_error_codes():
     case = make_case("diff_drive", 64, 5)
     ctl = CONTROLLERS["diff_drive"](horizon=5, num_samples=64)
