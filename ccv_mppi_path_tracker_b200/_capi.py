@@ -14,6 +14,8 @@ MODEL_DIFF_DRIVE, MODEL_STEERING, MODEL_FULL_BODY = 0, 1, 2
 DEBUG_NONE, DEBUG_NEAREST, DEBUG_STATES = 0, 1, 2
 SCAN_AUTO, SCAN_LITERAL, SCAN_PRUNED = 0, 1, 2
 WINDOW_AUTO, WINDOW_HOST, WINDOW_DEVICE = 0, 1, 2
+(OPT_GRID_MAX_CELLS, OPT_GRID_H_MIN, OPT_GRID_MARGIN, OPT_GRID_LANES, OPT_REDUCE_GROUPS, OPT_FUSE_CONTROLS,
+ OPT_NOISE_PREFETCH, OPT_EXCHANGE_TIMEOUT_MS, OPT_FEEDBACK_WARM_START, OPT_UPLOAD_WARM_START) = range(1, 11)
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
@@ -40,6 +42,8 @@ SYMBOLS = {
     "mppi_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "mppi_set_scan_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "mppi_set_window_builder": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppi_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "mppi_get_option": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),
     "mppi_set_path": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double), C.c_int]),
     "mppi_set_window": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_double)]),
     "mppi_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),

@@ -116,6 +116,15 @@ class _MPPIBase:
     def set_window_builder(self, mode):
         self._check(self.lib.mppi_set_window_builder(self._h, mode))
 
+    def set_option(self, option, value):
+        """mppi_set_option: tuning / behaviour switches (_capi.OPT_*)."""
+        self._check(self.lib.mppi_set_option(self._h, int(option), float(value)))
+
+    def get_option(self, option):
+        v = C.c_double(0.0)
+        self._check(self.lib.mppi_get_option(self._h, int(option), C.byref(v)))
+        return v.value
+
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.mppi_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

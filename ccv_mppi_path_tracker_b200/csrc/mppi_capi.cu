@@ -78,7 +78,10 @@ struct mppi_handle_s {
   bool staged_pending = false;
   // one pinned staging block mirroring d_in: header | windows | states | nominals
   char *h_in = nullptr, *d_in = nullptr;
-  size_t in_bytes = 0, nominal_off = 0;
+  size_t in_bytes = 0, state_off = 0, nominal_off = 0, window_off = 0;
+  size_t last_h2d_bytes = 0;       // what the last upload / solve copied host -> device
+  bool host_windows_staged = true; // the staged block carries host-built windows (must be copied)
+  int opt_upload_warm_start = 1;   // mppi_solve copies the caller's u_nominal to the device (0: keeps the device's own)
   float *h_out = nullptr, *d_out = nullptr;
   size_t out_bytes = 0;
   // host-side per-robot inputs
@@ -99,13 +102,21 @@ struct mppi_handle_s {
   double last_dt = 0.0;
   bool external_noise = false;
   bool weights_valid = false;  // d.weight holds the last solve's weights (false on the fused-controls path)
+  // options (mppi_set_option)
+  int opt_fuse_controls = -1, opt_prefetch = -1;
+  double opt_timeout_ms = 2000.0;
+  // noise prefetch: the current solve's normals are already in their buffer (generated beside the previous solve)
+  bool noise_primed = false;
+  bool last_fused = false;  // the kernel sequence issued (or captured) last reduces the controls inside K2
+  int sm_clock_khz = 1965000;
   int debug_flags = 0, scan_mode = MPPI_SCAN_AUTO;
   uint64_t seed = 0x5EED0000ull;
   int64_t sample_offset = 0, k_global = 0;
   int robot_offset = 0;
   // K0 (candidate grid) runs beside K1 (noise): they are independent
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_grid = nullptr, ev_join = nullptr, ev_k2done = nullptr, ev_epsfree = nullptr;
+  bool staged_recorded = false, k2_recorded = false;  // the events have been recorded on the current stream at least once
   // graphs
   bool use_graph = false;
   cudaGraphExec_t exec_kernels = nullptr, exec_solve = nullptr;
@@ -153,12 +164,8 @@ void invalidate_graphs(mppi_handle h) {
   h->exec_kernels = h->exec_solve = nullptr;
 }
 
-// K5 + K6 as one launch (one block per robot): unsharded handles whose partial arrays are small (latency path,
-// many-robot handles); large-K handles keep the wide finalize + merge pair
-bool fused_tail(mppi_handle h) { return h->n_ranks == 1 && (long long)h->d.planes * h->d.nchunk <= 4096; }
-
 // K3 folded into K4 (every K4 block recomputes the weights of its samples): pays off while K * planes is small
-bool fused_weights(const mppi_handle_s *h) { return h->K <= 32768; }
+bool fused_weights(const mppi_handle_s *h) { return h->K <= 32768; }  // re-measured in round 2: see DESIGN.md
 
 bool device_windows(mppi_handle h) {
   return h->window_builder == MPPI_WINDOW_DEVICE || (h->window_builder == MPPI_WINDOW_AUTO && h->R >= 8);
@@ -199,86 +206,137 @@ void fill_header(mppi_handle h, double dt) {
   hd->key1 = (uint32_t)(h->seed >> 32);
   hd->robot_offset = (uint32_t)h->robot_offset;
   hd->q_offset = (uint32_t)(h->sample_offset / 4);
+  // K2 takes the clamp bounds as a kernel parameter: keep them equal to the header's (a captured graph holds a copy)
+  ControlBounds b;
+  for (int u = 0; u < kMaxControls; ++u) {
+    b.lo[u] = hd->P.u_min[u];
+    b.hi[u] = hd->P.u_max[u];
+  }
+  if (memcmp(&b, &h->d.bounds, sizeof b) != 0) {
+    h->d.bounds = b;
+    invalidate_graphs(h);
+  }
 }
 
-// which nearest-point scan the next solve runs: the literal kernel is the one that records argmin indices
+// which nearest-point scan the next solve runs: the literal kernel is the one that records the predicted states
 int effective_scan(mppi_handle h, bool *want_nearest, bool *want_states = nullptr) {
   *want_nearest = (h->debug_flags & MPPI_DEBUG_NEAREST) && h->d.nearest;
   const bool ws = (h->debug_flags & MPPI_DEBUG_STATES) && h->d.states_dbg;
   if (want_states) *want_states = ws;
   int scan = h->scan_mode == MPPI_SCAN_AUTO ? MPPI_SCAN_PRUNED : h->scan_mode;
-  if (*want_nearest || ws || !pruned_scan_supported(h->d.T, h->d.planes)) scan = MPPI_SCAN_LITERAL;
+  if (ws || !pruned_scan_supported(h->d.T, h->d.planes) || !h->d.eps_map_valid) scan = MPPI_SCAN_LITERAL;
   return scan;
 }
 
-// K2 with the TMA ring also produces the weighted-control records of its CTAs (then K3 + K4 are replaced by the
-// small rescale kernel): the production path, i.e. the pruned scan without debug taps
+// K2 also produces the weighted-control records of its CTAs (then K3 + K4 are replaced by a rescale of the records).
+// AUTO: many-robot handles (K4 is far from the HBM roofline on many small tensors), and single solves whose K2 grid is
+// at most about two waves of CTAs but still covers the machine: there the CTAs' end phase runs in the shadow of the
+// slower CTAs of the same wave, while K3 + K4 would be two more dependent launches.  Large K keeps K4 (it runs at the
+// HBM roofline; the end phase would cost K2 what K4 saves), tiny K too (the pass would be serialised in a few CTAs).
 bool fused_controls(mppi_handle h, int scan) {
-  return scan == MPPI_SCAN_PRUNED && h->d.fuse_controls && h->d.cta_part && h->d.eps_map_valid && h->d.k2_ring == 1;
+  if (scan != MPPI_SCAN_PRUNED || !h->d.cta_part) return false;
+  if (h->opt_fuse_controls >= 0) return h->opt_fuse_controls != 0;
+  if (h->R >= 8) return true;
+  const long long ctas = (long long)h->R * ((h->K + 127) / 128);
+  return ctas >= 256 && ctas <= 2048;
 }
-// the finalize / merge kernels see cta_rescale_groups() partials per robot and plane on that path
-DeviceState tail_state(mppi_handle h, bool fused) {
-  DeviceState t = h->d;
-  if (fused) t.nb3 = t.nchunk = cta_rescale_groups((h->d.K + 127) / 128);
-  return t;
+// noise prefetch: needs the second buffer (allocated at mppi_create when it fits) and the internal generator; the
+// pruned scan only (its K0 resets the minimum-cost slot; the literal path is the debug / tiny-horizon path)
+bool prefetch_on(mppi_handle h, int scan) {
+  return h->d.eps_buffers == 2 && !h->external_noise && scan == MPPI_SCAN_PRUNED && h->opt_prefetch != 0;
 }
+// K5 + K6 as one launch (one block per robot): unsharded handles whose partial arrays are small (latency path,
+// many-robot handles); large-K handles keep the wide finalize + merge pair
 bool fused_tail_for(mppi_handle h, const DeviceState &t) {
   return h->n_ranks == 1 && (long long)t.planes * t.nchunk <= 4096;
 }
 
 // the kernel sequence of one solve on stream s (also what gets captured into the graph)
-int issue_kernels(mppi_handle h, cudaStream_t s) {
+//   main:  . . . . . . . . . . . . . . K2 -> (K3 -> K4 | -) -> tail (finalize / exchange / merge; counter++)
+//   side:  [K-1 window] -> K0 candidate grid -> K1 noise of the NEXT solve (prefetch)
+// K2 waits for K0; the tail waits for K1 (the generator reads the solve counter that the tail advances).
+// Plain stream launches (capturing = false) let the side stream start as soon as ITS inputs are there -- the staged
+// pose / window of this solve and the end of the previous solve's K2 (which reads the window and the grid) -- so the
+// window builder, the candidate grid and the generator run under the previous solve's K3 / K4 / tail.  Inside a
+// graph the side stream forks from the first node.
+int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   const DeviceState &d = h->d;
   int n = 0;
-  if (device_windows(h)) {
-    CU_TRY(h, launch_window_builder(d, s));
-    ++n;
-  }
   bool want_nearest, want_states;
   const int scan = effective_scan(h, &want_nearest, &want_states);
-  if (scan == MPPI_SCAN_PRUNED) {  // fork: the candidate grid (needs only the window) beside the noise generator
-    CU_TRY(h, cudaEventRecord(h->ev_fork, s));
-    CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    CU_TRY(h, launch_candidate_grid(d, h->side_stream));
-    CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+  const bool prefetch = prefetch_on(h, scan);
+  const bool dev_win = device_windows(h);
+  const bool side = scan == MPPI_SCAN_PRUNED;
+  cudaStream_t ws = side ? h->side_stream : s;  // where the window builder runs
+  if (side) {
+    if (capturing) {
+      CU_TRY(h, cudaEventRecord(h->ev_fork, s));
+      CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    } else {
+      if (h->staged_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->staged, 0));
+      if (h->k2_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_k2done, 0));
+    }
+  }
+  if (dev_win) {
+    CU_TRY(h, launch_window_builder(d, ws));
     ++n;
   }
-  if (h->external_noise) CU_TRY(h, launch_reset_cmin(d, s));
-  else CU_TRY(h, launch_noise(d, s));
-  ++n;
-  if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+  if (side) {
+    CU_TRY(h, launch_candidate_grid(d, h->side_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_grid, h->side_stream));
+    ++n;
+    if (prefetch) {
+      // the buffer of solve n+1 is the buffer of solve n-1: its last reader (K4, or the fused K2) must be done
+      if (!capturing && h->k2_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_epsfree, 0));
+      CU_TRY(h, launch_noise(d, 1, h->side_stream));
+      CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+      ++n;
+    }
+  }
+  if (!h->external_noise && !prefetch) {
+    CU_TRY(h, launch_noise(d, 0, s));
+    ++n;
+  }
+  if (side) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_grid, 0));
   const bool fused = fused_controls(h, scan);
   CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, fused, s));
   ++n;
+  if (!capturing) {
+    CU_TRY(h, cudaEventRecord(h->ev_k2done, s));
+    h->k2_recorded = true;
+  }
+  h->last_fused = fused;
   h->weights_valid = !fused;  // the per-sample weights are a debug tap on the fused path (mppi_get_weights)
-  if (fused) {
-    CU_TRY(h, launch_cta_rescale(d, s));
-    ++n;
-  } else {
+  if (!fused) {
     if (!fused_weights(h)) {
-      CU_TRY(h, launch_weights(d, s));
+      CU_TRY(h, launch_weights(d, false, s));
       ++n;
     }
     CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
     ++n;
   }
-  const DeviceState t = tail_state(h, fused);
-  if (h->p2p) {
-    CU_TRY(h, launch_finalize_push(t, s));
+  if (!capturing) CU_TRY(h, cudaEventRecord(h->ev_epsfree, s));  // the last reader of this solve's normals is queued
+  if (prefetch) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));  // join before the counter advances
+  h->launch_count = n;
+  if (fused) {  // rescale + finalize + merge (+ exchange) in one launch
+    const int mode = h->p2p ? 1 : (h->n_ranks > 1 ? 2 : 0);
+    CU_TRY(h, launch_rescale_tail(d, mode, s));
+    h->launch_count = ++n;
+    if (mode != 2) return MPPI_OK;
+  } else {
+    if (h->p2p) {
+      CU_TRY(h, launch_finalize_exchange(d, s));
+      h->launch_count = ++n;
+      return MPPI_OK;
+    }
+    if (fused_tail_for(h, d)) {
+      CU_TRY(h, launch_finalize_merge(d, s));
+      h->launch_count = ++n;
+      return MPPI_OK;
+    }
+    CU_TRY(h, launch_finalize(d, s));
     ++n;
-    CU_TRY(h, launch_merge_wait(t, s));
-    ++n;
-    h->launch_count = n;
-    return MPPI_OK;
   }
-  if (fused_tail_for(h, t)) {
-    CU_TRY(h, launch_finalize_merge(t, s));
-    ++n;
-    h->launch_count = n;
-    return MPPI_OK;
-  }
-  CU_TRY(h, launch_finalize(t, s));
-  ++n;
   if (h->n_ranks > 1) {
     int rc = g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s);
     if (rc != 0)
@@ -286,9 +344,26 @@ int issue_kernels(mppi_handle h, cudaStream_t s) {
                   std::string("ncclAllGather: ") + (g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "?"));
     ++n;
   }
-  CU_TRY(h, launch_merge(t, s));
-  ++n;
-  h->launch_count = n;
+  CU_TRY(h, launch_merge(d, s));
+  h->launch_count = ++n;
+  return MPPI_OK;
+}
+
+// Runs in front of a solve (outside any graph): with the prefetch on, the normals of the solve that is about to
+// run must already be in their buffer; they are not after mppi_create, mppi_set_seed, mppi_set_shard or a switch of
+// noise source / scan mode -- generate them now, in stream order before the solve.
+int prime_noise(mppi_handle h, bool header_staged_only) {
+  bool wn;
+  const int scan = effective_scan(h, &wn);
+  if (!prefetch_on(h, scan)) {
+    h->noise_primed = false;  // the next prefetching solve has to start from a fresh buffer
+    return MPPI_OK;
+  }
+  if (h->noise_primed) return MPPI_OK;
+  if (header_staged_only)  // the generator reads the shard offsets from the device header: bring it over first
+    CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, kHeaderBytes, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, launch_noise(h->d, 0, h->stream));
+  h->noise_primed = true;
   return MPPI_OK;
 }
 
@@ -307,12 +382,15 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
   // error the caller can see: the kernels' grid lookup and min() do not propagate NaN the way the FP64 loops do.
   for (size_t k = 0; k < (size_t)h->R * h->S; ++k)
     if (!std::isfinite(state[k])) return fail(h, MPPI_ERR_INVALID, "state must be finite");
+  if (u_nominal)  // a NaN warm start would live on in the device-resident controls for ever
+    for (size_t k = 0; k < (size_t)h->R * h->d.planes; ++k)
+      if (!std::isfinite(u_nominal[k])) return fail(h, MPPI_ERR_INVALID, "u_nominal (warm start) must be finite");
   int rc = wait_staging_free(h);
   if (rc) return rc;
   fill_header(h, dt);
   const DeviceState &d = h->d;
-  float *win = reinterpret_cast<float *>(h->h_in + kHeaderBytes);
-  float *st = win + (size_t)d.R * d.win_stride;
+  float *win = reinterpret_cast<float *>(h->h_in + h->window_off);
+  float *st = reinterpret_cast<float *>(h->h_in + h->state_off);
   float *nom = reinterpret_cast<float *>(h->h_in + h->nominal_off);
   double *st64 = reinterpret_cast<double *>(h->h_in + h->state64_off);
   const bool on_device = device_windows(h);
@@ -322,6 +400,7 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
   }
   memcpy(h->last_state.data(), state, sizeof(double) * (size_t)h->R * h->S);
   h->last_dt = dt;
+  h->host_windows_staged = !on_device;
   for (int r = 0; r < h->R; ++r) {
     const double *s = state + (size_t)r * h->S;
     double *w = h->window.data() + (size_t)r * h->T * 3;
@@ -332,8 +411,11 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
                                         dt, h->params.resolution, h->T, w);
     }
     // windows built on the device (K-1) overwrite this robot's slot after the H2D copy
-    if (!on_device || h->window_fixed[r]) window_to_robot_frame(w, h->T, s[0], s[1], win + (size_t)r * d.win_stride);
-    state_to_robot_frame(h->model, s, st + (size_t)r * 8);
+    if (!on_device || h->window_fixed[r]) {
+      window_to_robot_frame(w, h->T, s[0], s[1], win + (size_t)r * d.win_stride);
+      h->host_windows_staged = true;
+    }
+    state_to_robot_frame(h->model, s, st + (size_t)r * kStateStride);
     st64[2 * r] = s[0];
     st64[2 * r + 1] = s[1];
   }
@@ -344,15 +426,36 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
   return MPPI_OK;
 }
 
+// Host -> device copy of the staged block: always header + poses + state records; the warm start only when the host
+// supplies it; the windows only when they were built on the host (the device builder writes them in place).
+int enqueue_h2d(mppi_handle h, bool with_nominal, cudaStream_t s) {
+  const bool win = h->host_windows_staged;
+  size_t bytes = 0;
+  if (with_nominal) {
+    bytes = win ? h->in_bytes : h->window_off;
+    CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, bytes, cudaMemcpyHostToDevice, s));
+  } else {
+    bytes = h->nominal_off;
+    CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, bytes, cudaMemcpyHostToDevice, s));
+    if (win) {
+      CU_TRY(h, cudaMemcpyAsync(h->d_in + h->window_off, h->h_in + h->window_off, h->in_bytes - h->window_off,
+                                cudaMemcpyHostToDevice, s));
+      bytes += h->in_bytes - h->window_off;
+    }
+  }
+  h->last_h2d_bytes = bytes;
+  return MPPI_OK;
+}
+
+// graph replay: unsharded handles and the NVLink peer exchange (ordinary kernels); the NCCL transport keeps plain launches
+bool graph_capable(mppi_handle h) { return h->use_graph && (h->n_ranks == 1 || h->p2p); }
+
 int capture(mppi_handle h, bool with_copies, cudaGraphExec_t *out) {
   cudaGraph_t g = nullptr;
   CU_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int rc = MPPI_OK;
-  if (with_copies) {
-    cudaError_t e = cudaMemcpyAsync(h->d_in, h->h_in, h->in_bytes, cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
-  }
-  if (rc == MPPI_OK) rc = issue_kernels(h, h->stream);
+  if (with_copies) rc = enqueue_h2d(h, h->opt_upload_warm_start != 0, h->stream);
+  if (rc == MPPI_OK) rc = issue_kernels(h, h->stream, true);
   if (rc == MPPI_OK && with_copies) {
     cudaError_t e = cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream);
     if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
@@ -369,13 +472,23 @@ int capture(mppi_handle h, bool with_copies, cudaGraphExec_t *out) {
   return MPPI_OK;
 }
 
+// the merge of the peer exchange flags a record that did not arrive in stats[3] (h_out holds a fresh copy of d_out)
+int exchange_status(mppi_handle h) {
+  if (!h->p2p) return MPPI_OK;
+  const size_t n = (size_t)h->R * h->d.planes;
+  for (int r = 0; r < h->R; ++r)
+    if (h->h_out[n + (size_t)r * 4 + 3] != 0.f)
+      return fail(h, MPPI_ERR_NCCL,
+                  "peer exchange timed out: a rank's record did not arrive (are all ranks solving?); controls and warm "
+                  "start keep their previous values");
+  return MPPI_OK;
+}
+
 int copy_out(mppi_handle h, double *u_nominal) {
+  int rc = exchange_status(h);
+  if (rc) return rc;
   const size_t n = (size_t)h->R * h->d.planes;
   for (size_t k = 0; k < n; ++k) u_nominal[k] = (double)h->h_out[k];
-  if (h->p2p)
-    for (int r = 0; r < h->R; ++r)
-      if (h->h_out[n + (size_t)r * 4 + 3] != 0.f)
-        return fail(h, MPPI_ERR_NCCL, "peer exchange timed out: a rank's record did not arrive (are all ranks solving?)");
   return MPPI_OK;
 }
 
@@ -433,11 +546,6 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   // candidate grid of the pruned scan: building it costs ~cells*T distance evaluations per robot and solve, the
   // rollouts K*T*(~100 instr): keep the grid below a few per cent of that
   d.grid_max_cells = num_samples / 2 < 256 ? 256 : (num_samples / 2 > 65536 ? 65536 : num_samples / 2);
-  if (const char *e = getenv("MPPI_GRID_MAX_CELLS")) d.grid_max_cells = atoi(e);  // tuning experiments only
-  if (const char *e = getenv("MPPI_GRID_H_MIN")) d.grid_h_min = (float)atof(e);
-  if (const char *e = getenv("MPPI_GRID_MARGIN")) d.grid_margin = (float)atof(e);
-  if (const char *e = getenv("MPPI_K0_LANES")) d.grid_lanes = atoi(e);
-  if (const char *e = getenv("MPPI_K4_GROUPS")) d.k4_groups = atoi(e);
   if (d.planes > 65535) {
     delete h;
     return fail(nullptr, MPPI_ERR_INVALID, "(horizon-1)*U exceeds 65535");
@@ -454,19 +562,31 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
     if (e__ != cudaSuccess) return bail(MPPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
   CU_NEW(cudaSetDevice(device));
-  CU_NEW(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  // the solve's own kernels go first when they compete for SMs with the side stream's candidate grid / noise prefetch
+  int prio_least = 0, prio_greatest = 0;
+  CU_NEW(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CU_NEW(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_greatest));
   h->stream = h->own_stream;
   CU_NEW(cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming));
-  CU_NEW(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CU_NEW(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_least));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_grid, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_k2done, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_epsfree, cudaEventDisableTiming));
+  CU_NEW(cudaDeviceGetAttribute(&h->sm_clock_khz, cudaDevAttrClockRate, device));
+  if (h->sm_clock_khz <= 0) h->sm_clock_khz = 1965000;
+  d.xchg_timeout_cycles = (long long)(h->opt_timeout_ms * (double)h->sm_clock_khz);
 
+  // staging block: header | pose (FP64 x, y) | state record | warm start | windows -- a solve copies the prefix it needs
   const size_t win_bytes = sizeof(float) * (size_t)d.R * d.win_stride;
-  const size_t st_bytes = sizeof(float) * (size_t)d.R * 8;
+  const size_t st_bytes = sizeof(float) * (size_t)d.R * kStateStride;
   const size_t nom_bytes = sizeof(float) * (size_t)d.R * d.planes;
-  h->nominal_off = align_up(kHeaderBytes + win_bytes + st_bytes, 16);
-  h->state64_off = align_up(h->nominal_off + nom_bytes, 16);
-  h->in_bytes = align_up(h->state64_off + sizeof(double) * 2 * (size_t)d.R, 16);
+  h->state64_off = kHeaderBytes;
+  h->state_off = h->state64_off + sizeof(double) * 2 * (size_t)d.R;
+  h->nominal_off = align_up(h->state_off + st_bytes, 16);
+  h->window_off = align_up(h->nominal_off + nom_bytes, 16);
+  h->in_bytes = align_up(h->window_off + win_bytes, 16);
   h->out_bytes = sizeof(float) * ((size_t)d.R * d.planes + (size_t)d.R * 4);
   CU_NEW(cudaMallocHost((void **)&h->h_in, h->in_bytes));
   CU_NEW(cudaMallocHost((void **)&h->h_out, h->out_bytes));
@@ -477,8 +597,8 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&h->d_out, h->out_bytes));
   CU_NEW(cudaMemset(h->d_out, 0, h->out_bytes));
   d.hdr = reinterpret_cast<SolveHeader *>(h->d_in);
-  d.window = reinterpret_cast<float *>(h->d_in + kHeaderBytes);
-  d.state = d.window + (size_t)d.R * d.win_stride;
+  d.window = reinterpret_cast<float *>(h->d_in + h->window_off);
+  d.state = reinterpret_cast<float *>(h->d_in + h->state_off);
   d.nominal = reinterpret_cast<float *>(h->d_in + h->nominal_off);
   d.state64 = reinterpret_cast<double *>(h->d_in + h->state64_off);
   CU_NEW(cudaMalloc((void **)&h->d_path_off, sizeof(int) * ((size_t)d.R + 1)));
@@ -491,7 +611,14 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   d.win_fixed = h->d_win_fixed;
   d.u_new = h->d_out;
   d.stats = h->d_out + (size_t)d.R * d.planes;
-  CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
+  // noise tensor: two buffers (the next solve's normals are generated beside the current solve) when both fit easily
+  d.eps_buf_elems = (size_t)d.R * d.planes * d.Kp;
+  {
+    size_t free_b = 0, total_b = 0;
+    CU_NEW(cudaMemGetInfo(&free_b, &total_b));
+    d.eps_buffers = (2 * sizeof(float) * d.eps_buf_elems <= free_b / 2) ? 2 : 1;
+  }
+  CU_NEW(cudaMalloc((void **)&d.eps, sizeof(float) * d.eps_buffers * d.eps_buf_elems));
   CU_NEW(cudaMalloc((void **)&d.cost, sizeof(float) * (size_t)d.R * d.K));
   CU_NEW(cudaMalloc((void **)&d.weight, sizeof(float) * (size_t)d.R * d.K));
   const int nb3_weights = d.nb3;  // blocks of the stand-alone weight kernel (also the on-demand weights tap)
@@ -499,19 +626,24 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * (nb3_weights > d.nb3 ? nb3_weights : d.nb3) * 2));
   CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.planes * d.nchunk));
   CU_NEW(cudaMalloc((void **)&d.record, sizeof(float) * (size_t)d.R * d.rec_stride));
-  // Weighted controls inside K2 (per-CTA records) instead of K3 + K4: measured -7 % per solve for 1024 robots x
-  // K = 1024 (K4 is far from the HBM roofline on many small tensors), +1.5 % at K = 2^20 (K4 alone runs at the
-  // roofline; the CTAs' end phase costs K2 more than K4 saves) and +30..80 % on the latency configurations (the
-  // pass is serialised inside a few CTAs) -- so: many-robot handles only.
-  d.fuse_controls = n_robots >= 8;
-  if (const char *e = getenv("MPPI_FUSE_CONTROLS")) d.fuse_controls = atoi(e) != 0;  // tuning experiments / tests
+  // per-CTA records of the fused weighted controls (fused_controls() decides per solve whether K2 writes them)
   CU_NEW(cudaMalloc((void **)&d.cta_part, sizeof(float) * (size_t)d.R * ((d.K + 127) / 128) * d.rec_stride));
+  CU_NEW(cudaMalloc((void **)&d.tail_ticket, sizeof(unsigned int) * ((size_t)d.R + 1)));
+  CU_NEW(cudaMemset(d.tail_ticket, 0, sizeof(unsigned int) * ((size_t)d.R + 1)));
   CU_NEW(cudaMalloc((void **)&d.cmin, sizeof(unsigned int) * (size_t)d.R));
+  CU_NEW(cudaMemset(d.cmin, 0xFF, sizeof(unsigned int) * (size_t)d.R));  // armed; every solve's tail re-arms it
   CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
-  CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * (size_t)d.R * d.planes * d.Kp));
-  CU_NEW(make_eps_tensor_map(d));
-  if (const char *e = getenv("MPPI_K2_RING")) d.k2_ring = atoi(e);  // tuning experiments only
+  CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * d.eps_buffers * d.eps_buf_elems));
+  if (make_eps_tensor_map(d) != cudaSuccess) d.eps_map_valid = false;  // no TMA descriptor: the literal scan runs
+  if (pruned_scan_supported(d.T, d.planes)) d.side_carveout = rollout_carveout_percent(d);
+  {
+    const SolveParams P0 = make_solve_params(model, horizon, *params, 0.1);
+    for (int u = 0; u < kMaxControls; ++u) {
+      d.bounds.lo[u] = P0.u_min[u];
+      d.bounds.hi[u] = P0.u_max[u];
+    }
+  }
   CU_NEW(cudaMalloc((void **)&d.grid_hdr, sizeof(GridHeader) * (size_t)d.R));
   CU_NEW(cudaMemset(d.grid_hdr, 0, sizeof(GridHeader) * (size_t)d.R));
   CU_NEW(cudaMalloc((void **)&d.grid_cells, sizeof(uint32_t) * (size_t)d.R * d.grid_max_cells));
@@ -539,7 +671,8 @@ int mppi_destroy(mppi_handle h) {
   DeviceState &d = h->d;
   if (d.gathered && d.gathered != d.record) cudaFree(d.gathered);
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
-  cudaFree(d.record); cudaFree(d.cta_part); cudaFree(d.cmin); cudaFree(d.counter); cudaFree(d.nearest);
+  cudaFree(d.record); cudaFree(d.cta_part); cudaFree(d.tail_ticket); cudaFree(d.cmin); cudaFree(d.counter);
+  cudaFree(d.nearest);
   cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg);
   cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
   cudaFree(h->d_in); cudaFree(h->d_out);
@@ -547,7 +680,10 @@ int mppi_destroy(mppi_handle h) {
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->staged) cudaEventDestroy(h->staged);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_grid) cudaEventDestroy(h->ev_grid);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_k2done) cudaEventDestroy(h->ev_k2done);
+  if (h->ev_epsfree) cudaEventDestroy(h->ev_epsfree);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -596,6 +732,93 @@ int mppi_set_window_builder(mppi_handle h, int mode) {
   return MPPI_OK;
 }
 
+int mppi_set_option(mppi_handle h, int option, double value) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!std::isfinite(value)) return fail(h, MPPI_ERR_INVALID, "option value must be finite");
+  const long long iv = (long long)value;
+  const bool integral = (double)iv == value;
+  DeviceState &d = h->d;
+  switch (option) {
+    case MPPI_OPT_GRID_MAX_CELLS: {
+      if (!integral || iv < 256 || iv > 262144) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_GRID_MAX_CELLS: 256 .. 262144");
+      if ((int)iv == d.grid_max_cells) return MPPI_OK;
+      CU_TRY(h, cudaSetDevice(h->device));
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+      uint32_t *cells = nullptr;
+      CU_TRY(h, cudaMalloc((void **)&cells, sizeof(uint32_t) * (size_t)d.R * (size_t)iv));
+      cudaFree(d.grid_cells);
+      d.grid_cells = cells;
+      d.grid_max_cells = (int)iv;
+      break;
+    }
+    case MPPI_OPT_GRID_H_MIN:
+      if (!(value > 0.0)) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_GRID_H_MIN: > 0");
+      d.grid_h_min = (float)value;
+      break;
+    case MPPI_OPT_GRID_MARGIN:
+      if (value < 0.0) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_GRID_MARGIN: >= 0 (0 = automatic)");
+      d.grid_margin = (float)value;
+      break;
+    case MPPI_OPT_GRID_LANES:
+      if (!integral || !(iv == 0 || iv == 1 || iv == 2 || iv == 4 || iv == 8 || iv == 16 || iv == 32))
+        return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_GRID_LANES: 0 (automatic), 1, 2, 4, 8, 16 or 32");
+      d.grid_lanes = (int)iv;
+      break;
+    case MPPI_OPT_REDUCE_GROUPS:
+      if (!integral || iv < 0 || iv > 65535) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_REDUCE_GROUPS: 0 (automatic) .. 65535");
+      d.k4_groups = (int)iv;
+      break;
+    case MPPI_OPT_FUSE_CONTROLS:
+      if (!integral || iv < -1 || iv > 1) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_FUSE_CONTROLS: -1 (automatic), 0 or 1");
+      h->opt_fuse_controls = (int)iv;
+      break;
+    case MPPI_OPT_NOISE_PREFETCH:
+      if (!integral || iv < -1 || iv > 1) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_NOISE_PREFETCH: -1 (automatic), 0 or 1");
+      if (iv == 1 && d.eps_buffers < 2)
+        return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_NOISE_PREFETCH: the second noise buffer did not fit at mppi_create");
+      h->opt_prefetch = (int)iv;
+      h->noise_primed = false;
+      break;
+    case MPPI_OPT_EXCHANGE_TIMEOUT_MS:
+      if (!(value >= 1.0 && value <= 600000.0)) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_EXCHANGE_TIMEOUT_MS: 1 .. 600000");
+      h->opt_timeout_ms = value;
+      d.xchg_timeout_cycles = (long long)(value * (double)h->sm_clock_khz);
+      break;
+    case MPPI_OPT_FEEDBACK_WARM_START:
+      if (!integral || iv < 0 || iv > 1) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_FEEDBACK_WARM_START: 0 or 1");
+      d.feedback = iv != 0;
+      break;
+    case MPPI_OPT_UPLOAD_WARM_START:
+      if (!integral || iv < 0 || iv > 1) return fail(h, MPPI_ERR_INVALID, "MPPI_OPT_UPLOAD_WARM_START: 0 or 1");
+      h->opt_upload_warm_start = (int)iv;
+      break;
+    default:
+      return fail(h, MPPI_ERR_INVALID, "unknown option");
+  }
+  invalidate_graphs(h);  // every option is a kernel argument or changes the kernel sequence
+  return MPPI_OK;
+}
+
+int mppi_get_option(mppi_handle h, int option, double *value) {
+  if (!h) return MPPI_ERR_INVALID;
+  if (!value) return fail(h, MPPI_ERR_INVALID, "value is NULL");
+  const DeviceState &d = h->d;
+  switch (option) {
+    case MPPI_OPT_GRID_MAX_CELLS: *value = d.grid_max_cells; break;
+    case MPPI_OPT_GRID_H_MIN: *value = d.grid_h_min; break;
+    case MPPI_OPT_GRID_MARGIN: *value = d.grid_margin; break;
+    case MPPI_OPT_GRID_LANES: *value = d.grid_lanes; break;
+    case MPPI_OPT_REDUCE_GROUPS: *value = d.k4_groups; break;
+    case MPPI_OPT_FUSE_CONTROLS: *value = h->opt_fuse_controls; break;
+    case MPPI_OPT_NOISE_PREFETCH: *value = h->opt_prefetch; break;
+    case MPPI_OPT_EXCHANGE_TIMEOUT_MS: *value = h->opt_timeout_ms; break;
+    case MPPI_OPT_FEEDBACK_WARM_START: *value = d.feedback ? 1.0 : 0.0; break;
+    case MPPI_OPT_UPLOAD_WARM_START: *value = h->opt_upload_warm_start; break;
+    default: return fail(h, MPPI_ERR_INVALID, "unknown option");
+  }
+  return MPPI_OK;
+}
+
 int mppi_set_path(mppi_handle h, int robot, const double *path_xy, int n_points) {
   if (!h) return MPPI_ERR_INVALID;
   if (robot < 0 || robot >= h->R || n_points < 1 || !path_xy) return fail(h, MPPI_ERR_INVALID, "bad robot index or empty path");
@@ -625,6 +848,7 @@ int mppi_set_seed(mppi_handle h, uint64_t seed, uint64_t first_solve_counter) {
   uint32_t c = (uint32_t)first_solve_counter;
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   CU_TRY(h, cudaMemcpy(h->d.counter, &c, sizeof c, cudaMemcpyHostToDevice));
+  h->noise_primed = false;
   return MPPI_OK;
 }
 
@@ -635,6 +859,7 @@ int mppi_set_shard(mppi_handle h, int64_t sample_offset, int64_t num_samples_glo
   h->sample_offset = sample_offset;
   h->k_global = num_samples_global;
   h->robot_offset = robot_offset;
+  h->noise_primed = false;
   return MPPI_OK;
 }
 
@@ -644,17 +869,20 @@ int mppi_set_noise(mppi_handle h, const float *eps) {
   const bool ext = eps != nullptr;
   if (ext != h->external_noise) invalidate_graphs(h);
   h->external_noise = ext;
+  h->noise_primed = false;
   if (!ext) return MPPI_OK;
   const DeviceState &d = h->d;
   const int K = h->K, U = h->U, steps = h->T - 1;
-  std::vector<float> phys((size_t)d.R * d.planes * d.Kp, 0.f);
+  std::vector<float> phys(d.eps_buf_elems, 0.f);
   for (int r = 0; r < d.R; ++r)
     for (int t = 0; t < steps; ++t)
       for (int i = 0; i < K; ++i)
         for (int u = 0; u < U; ++u)
           phys[((size_t)r * d.planes + (size_t)t * U + u) * d.Kp + i] = eps[(((size_t)r * steps + t) * K + i) * U + u];
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  CU_TRY(h, cudaMemcpy(d.eps, phys.data(), sizeof(float) * phys.size(), cudaMemcpyHostToDevice));
+  for (int b = 0; b < d.eps_buffers; ++b)  // the same tensor for every following solve, whichever buffer it reads
+    CU_TRY(h, cudaMemcpy(d.eps + (size_t)b * d.eps_buf_elems, phys.data(), sizeof(float) * phys.size(),
+                         cudaMemcpyHostToDevice));
   return MPPI_OK;
 }
 
@@ -662,6 +890,7 @@ int mppi_set_stream(mppi_handle h, void *cuda_stream) {
   if (!h) return MPPI_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->side_stream) CU_TRY(h, cudaStreamSynchronize(h->side_stream));
   invalidate_graphs(h);
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   return MPPI_OK;
@@ -679,30 +908,38 @@ int mppi_upload(mppi_handle h, const double *state, double dt, const double *u_n
   CU_TRY(h, cudaSetDevice(h->device));
   int rc = stage_inputs(h, state, dt, u_nominal);
   if (rc) return rc;
-  CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, u_nominal ? h->in_bytes : h->nominal_off, cudaMemcpyHostToDevice, h->stream));
-  if (!u_nominal)  // keep the device-resident warm start: skip the nominal slot, copy the FP64 poses behind it
-    CU_TRY(h, cudaMemcpyAsync(h->d_in + h->state64_off, h->h_in + h->state64_off, h->in_bytes - h->state64_off,
-                              cudaMemcpyHostToDevice, h->stream));
+  rc = enqueue_h2d(h, u_nominal != nullptr, h->stream);  // u_nominal == NULL keeps the device-resident warm start
+  if (rc) return rc;
   CU_TRY(h, cudaEventRecord(h->staged, h->stream));
   h->staged_pending = true;
+  h->staged_recorded = true;
   h->have_inputs = true;
   if (u_nominal) h->have_nominal = true;
   return MPPI_OK;
+}
+
+static int issue_kernels_primed(mppi_handle h) {
+  int rc = prime_noise(h, false);
+  if (rc) return rc;
+  return issue_kernels(h, h->stream, false);
 }
 
 int mppi_enqueue(mppi_handle h) {
   if (!h) return MPPI_ERR_INVALID;
   if (!h->have_inputs) return fail(h, MPPI_ERR_STATE, "mppi_enqueue before mppi_upload");
   CU_TRY(h, cudaSetDevice(h->device));
-  if (h->use_graph && h->n_ranks == 1) {
+  int rc = prime_noise(h, false);
+  if (rc) return rc;
+  if (graph_capable(h)) {
     if (!h->exec_kernels) {
-      int rc = capture(h, false, &h->exec_kernels);
+      rc = capture(h, false, &h->exec_kernels);
       if (rc) return rc;
     }
     CU_TRY(h, cudaGraphLaunch(h->exec_kernels, h->stream));
+    h->weights_valid = !h->last_fused;  // a replay overwrites the costs: weights of an earlier solve are stale
     return MPPI_OK;
   }
-  return issue_kernels(h, h->stream);
+  return issue_kernels(h, h->stream, false);
 }
 
 int mppi_download(mppi_handle h, double *u_nominal) {
@@ -718,30 +955,42 @@ int mppi_download(mppi_handle h, double *u_nominal) {
 int mppi_synchronize(mppi_handle h) {
   if (!h) return MPPI_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
+  if (h->p2p) {  // bring the statistics over: a peer-exchange time-out of an enqueued solve is reported here too
+    const size_t off = sizeof(float) * (size_t)h->R * h->d.planes;
+    CU_TRY(h, cudaMemcpyAsync((char *)h->h_out + off, (char *)h->d_out + off, h->out_bytes - off, cudaMemcpyDeviceToHost,
+                              h->stream));
+  }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->staged_pending = false;
-  return MPPI_OK;
+  return exchange_status(h);
 }
 
 int mppi_solve(mppi_handle h, const double *state, double dt, double *u_nominal) {
   if (!h) return MPPI_ERR_INVALID;
   if (!u_nominal) return fail(h, MPPI_ERR_INVALID, "u_nominal is NULL");
   CU_TRY(h, cudaSetDevice(h->device));
-  if (h->use_graph && h->n_ranks == 1) {
-    int rc = stage_inputs(h, state, dt, u_nominal);
+  // MPPI_OPT_UPLOAD_WARM_START = 0: after the first solve the warm start is the device's own copy of the previous
+  // result (what the reference's optimal_solution is when the host does not touch it between cycles)
+  const bool with_nominal = h->opt_upload_warm_start != 0 || !h->have_nominal;
+  if (graph_capable(h) && with_nominal == (h->opt_upload_warm_start != 0)) {
+    int rc = stage_inputs(h, state, dt, with_nominal ? u_nominal : nullptr);
+    if (rc) return rc;
+    rc = prime_noise(h, true);
     if (rc) return rc;
     if (!h->exec_solve) {
       rc = capture(h, true, &h->exec_solve);
       if (rc) return rc;
     }
     CU_TRY(h, cudaGraphLaunch(h->exec_solve, h->stream));
+    h->weights_valid = !h->last_fused;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_inputs = h->have_nominal = true;
     return copy_out(h, u_nominal);
   }
-  int rc = mppi_upload(h, state, dt, u_nominal);
+  int rc = mppi_upload(h, state, dt, with_nominal ? u_nominal : nullptr);
   if (rc) return rc;
-  rc = mppi_enqueue(h);
+  if (graph_capable(h)) rc = issue_kernels_primed(h);  // a one-off solve in front of the graph: plain launches
+  else rc = mppi_enqueue(h);
   if (rc) return rc;
   return mppi_download(h, u_nominal);
 }
@@ -762,7 +1011,7 @@ int mppi_get_weights(mppi_handle h, int robot, float *weights) {
   if (!h->weights_valid) {  // fused-controls path: exp(-(c - c_min)/lambda) from the resident costs, on demand
     DeviceState t = h->d;
     t.nb3 = (h->K + kWeightBlock * 4 - 1) / (kWeightBlock * 4);
-    CU_TRY(h, launch_weights(t, h->stream));
+    CU_TRY(h, launch_weights(t, true, h->stream));
     h->weights_valid = true;
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -814,8 +1063,11 @@ int mppi_get_noise(mppi_handle h, int robot, float *eps) {
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   const DeviceState &d = h->d;
   std::vector<float> phys((size_t)d.planes * d.Kp);
-  CU_TRY(h, cudaMemcpy(phys.data(), d.eps + (size_t)robot * d.planes * d.Kp, sizeof(float) * phys.size(),
-                       cudaMemcpyDeviceToHost));
+  uint32_t counter = 0;  // the merge has advanced it: the last solve used buffer (counter - 1) & (buffers - 1)
+  CU_TRY(h, cudaMemcpy(&counter, d.counter, sizeof counter, cudaMemcpyDeviceToHost));
+  const size_t buf = (size_t)((counter - 1u) & (uint32_t)(d.eps_buffers - 1));
+  CU_TRY(h, cudaMemcpy(phys.data(), d.eps + buf * d.eps_buf_elems + (size_t)robot * d.planes * d.Kp,
+                       sizeof(float) * phys.size(), cudaMemcpyDeviceToHost));
   const int K = h->K, U = h->U, steps = h->T - 1;
   for (int t = 0; t < steps; ++t)
     for (int i = 0; i < K; ++i)
@@ -877,7 +1129,7 @@ int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int
 
 int mppi_get_io_bytes(mppi_handle h, size_t *h2d_bytes, size_t *d2h_bytes) {
   if (!h) return MPPI_ERR_INVALID;
-  if (h2d_bytes) *h2d_bytes = h->in_bytes;
+  if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes ? h->last_h2d_bytes : h->in_bytes;
   if (d2h_bytes) *d2h_bytes = h->out_bytes;
   return MPPI_OK;
 }
@@ -887,62 +1139,74 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
   if (n_iters < 1 || !ms) return fail(h, MPPI_ERR_INVALID, "n_iters >= 1 and ms != NULL required");
   if (!h->have_inputs) return fail(h, MPPI_ERR_STATE, "mppi_time_kernels before mppi_upload");
   CU_TRY(h, cudaSetDevice(h->device));
-  cudaEvent_t ev[9];
+  cudaEvent_t ev[9] = {};
+  struct EventGuard {  // destroyed on every exit path
+    cudaEvent_t *e;
+    ~EventGuard() {
+      for (int k = 0; k < 9; ++k)
+        if (e[k]) cudaEventDestroy(e[k]);
+    }
+  } guard{ev};
   for (auto &e : ev) CU_TRY(h, cudaEventCreate(&e));
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const DeviceState &d = h->d;
   cudaStream_t s = h->stream;
   bool want_nearest;
   const int scan = effective_scan(h, &want_nearest);
-  int rc = MPPI_OK;
-  for (int it = 0; it <= n_iters && rc == MPPI_OK; ++it) {
-    if (device_windows(h)) launch_window_builder(d, s);
-    cudaEventRecord(ev[0], s);
-    if (h->external_noise) launch_reset_cmin(d, s); else launch_noise(d, s);
-    cudaEventRecord(ev[1], s);
-    if (scan == MPPI_SCAN_PRUNED) launch_candidate_grid(d, s);
-    cudaEventRecord(ev[7], s);
+  h->noise_primed = false;  // the generator runs in front of its own solve here
+  for (int it = 0; it <= n_iters; ++it) {
+    if (device_windows(h)) CU_TRY(h, launch_window_builder(d, s));
+    CU_TRY(h, cudaEventRecord(ev[0], s));
+    if (!h->external_noise) CU_TRY(h, launch_noise(d, 0, s));
+    CU_TRY(h, cudaEventRecord(ev[1], s));
+    if (scan == MPPI_SCAN_PRUNED) CU_TRY(h, launch_candidate_grid(d, s));
+    CU_TRY(h, cudaEventRecord(ev[7], s));
     const bool fc = fused_controls(h, scan);
-    launch_rollout_cost(d, scan, want_nearest, false, fc, s);
-    cudaEventRecord(ev[2], s);
+    CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, false, fc, s));
+    CU_TRY(h, cudaEventRecord(ev[2], s));
+    h->last_fused = fc;
     h->weights_valid = !fc;
-    if (fc) launch_cta_rescale(d, s);  // reported in the "weights" slot; "weighted_controls" is then 0
-    else if (!fused_weights(h)) launch_weights(d, s);
-    cudaEventRecord(ev[3], s);
-    if (!fc) launch_weighted_controls(d, fused_weights(h), s);
-    cudaEventRecord(ev[4], s);
-    const DeviceState ts = tail_state(h, fc);
-    const bool fused = fused_tail_for(h, ts);
-    if (h->p2p) launch_finalize_push(ts, s);
-    else if (fused) launch_finalize_merge(ts, s);
-    else launch_finalize(ts, s);
-    cudaEventRecord(ev[5], s);
-    if (h->p2p) {
-      launch_merge_wait(ts, s);
-    } else if (!fused) {
+    if (!fc && !fused_weights(h)) CU_TRY(h, launch_weights(d, false, s));
+    CU_TRY(h, cudaEventRecord(ev[3], s));
+    if (!fc) CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
+    CU_TRY(h, cudaEventRecord(ev[4], s));
+    // tail: reported as "finalize" (+ "merge" where that is a launch of its own)
+    bool merge_follows = false;
+    if (fc) {
+      const int mode = h->p2p ? 1 : (h->n_ranks > 1 ? 2 : 0);
+      CU_TRY(h, launch_rescale_tail(d, mode, s));
+      merge_follows = mode == 2;
+    } else if (h->p2p) {
+      CU_TRY(h, launch_finalize_exchange(d, s));
+    } else if (fused_tail_for(h, d)) {
+      CU_TRY(h, launch_finalize_merge(d, s));
+    } else {
+      CU_TRY(h, launch_finalize(d, s));
+      merge_follows = true;
+    }
+    CU_TRY(h, cudaEventRecord(ev[5], s));
+    if (merge_follows) {
       if (h->n_ranks > 1 &&
           g_nccl.all_gather(d.record, d.gathered, (size_t)d.R * d.rec_stride, kNcclFloat, h->comm, s) != 0)
-        rc = fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
-      launch_merge(ts, s);
+        return fail(h, MPPI_ERR_NCCL, "ncclAllGather failed");
+      CU_TRY(h, launch_merge(d, s));
     }
-    cudaEventRecord(ev[6], s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
-    if (it == 0 || rc != MPPI_OK) continue;  // warm-up
+    CU_TRY(h, cudaEventRecord(ev[6], s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    if (it == 0) continue;  // warm-up
     for (int k = 0; k < 6; ++k) {
       float t = 0.f;
-      cudaEventElapsedTime(&t, k == 1 ? ev[7] : ev[k], ev[k + 1]);
+      CU_TRY(h, cudaEventElapsedTime(&t, k == 1 ? ev[7] : ev[k], ev[k + 1]));
       acc[k] += t;
     }
     float t = 0.f;
-    cudaEventElapsedTime(&t, ev[0], ev[6]);
+    CU_TRY(h, cudaEventElapsedTime(&t, ev[0], ev[6]));
     acc[6] += t;
-    cudaEventElapsedTime(&t, ev[1], ev[7]);
+    CU_TRY(h, cudaEventElapsedTime(&t, ev[1], ev[7]));
     acc[7] += t;
   }
-  for (auto &e : ev) cudaEventDestroy(e);
   for (int k = 0; k < 8; ++k) ms[k] = (float)(acc[k] / n_iters);
-  return rc;
+  return MPPI_OK;
 }
 
 int mppi_last_launch_count(mppi_handle h) { return h ? h->launch_count : 0; }

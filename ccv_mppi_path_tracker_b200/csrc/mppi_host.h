@@ -97,14 +97,13 @@ inline void window_to_robot_frame(const double *window, int T, double px, double
   }
 }
 
-// state record {0, 0, yaw, roll, pitch, 0, 0, 0}  (yaw_ref_[0] is derived from the FP32 window by the kernels)
+// state record {yaw, roll, pitch, 0}: the kernels work in the robot-centred frame (x = y = 0); yaw_ref_[0] is derived
+// from the FP32 window by the kernels
 inline void state_to_robot_frame(int model, const double *state, float *out) {
-  out[0] = 0.f;
-  out[1] = 0.f;
-  out[2] = (float)state[2];
-  out[3] = model == kFullBody ? (float)state[3] : 0.f;
-  out[4] = model == kFullBody ? (float)state[4] : 0.f;
-  out[5] = out[6] = out[7] = 0.f;
+  out[0] = (float)state[2];
+  out[1] = model == kFullBody ? (float)state[3] : 0.f;
+  out[2] = model == kFullBody ? (float)state[4] : 0.f;
+  out[3] = 0.f;
 }
 
 }  // namespace mppi

@@ -22,6 +22,12 @@ struct SolveHeader {
   double v_ref64, dt64, resolution64;
 };
 
+// clamp bounds of the controls (DD:24-26, :98-99) as a kernel parameter of K2: constant-bank operands instead of
+// registers.  Same FP32 values as SolveParams::u_min / u_max (make_solve_params).
+struct ControlBounds {
+  float lo[kMaxControls], hi[kMaxControls];
+};
+
 // geometry of one robot's candidate grid (written by K0, read by K2): cell (ix, iy) = floor(fma(x, inv_h, cx)), ...
 struct GridHeader {
   float x0, y0, h, inv_h, cx, cy;
@@ -29,16 +35,21 @@ struct GridHeader {
 };
 
 // HBM layout owned by one handle.  R robots, K samples (this shard), T horizon, U controls, P = (T-1)*U planes.
-//   inbuf    one allocation, one H2D copy per solve:
+//   inbuf    one allocation; a solve copies the prefix it needs (host -> device), in this order:
 //     hdr      SolveHeader (padded to 256 B)
-//     state64  [R][2]    pose x, y in FP64 (device-side window builder only; after nominal)
-//     window   [R][WS]   WS floats: T x {x_ref - x0, y_ref - y0} (robot-centred frame, FP32), padded to 16 B
-//     state    [R][8]    {0, 0, yaw, roll, pitch, yaw_ref[0], -, -}
-//     nominal  [R][P]    warm start u*; the merge kernel overwrites it in place with the new controls
-//   eps      [R][P][Kp]  standard normals, plane-major: one warp reads 32 consecutive samples of one (t,u)
-//                        plane (128 B coalesced); Kp = K rounded up to 4 (float4 stores of the generator)
+//     state64  [R][2]    pose x, y in FP64 (device-side window builder)
+//     state    [R][4]    {yaw, roll, pitch, -} (the kernels work in the robot-centred frame: x = y = 0)
+//     nominal  [R][P]    warm start u*; the merge kernel overwrites it in place with the new controls.  Copied only
+//                        when the host supplies the warm start (mppi_upload with u_nominal, MPPI_OPT_UPLOAD_WARM_START)
+//     window   [R][WS]   WS floats: T x {x_ref - x0, y_ref - y0} (robot-centred frame, FP32), padded to 16 B.  Copied
+//                        only when windows are built on the host; the device builder (K-1) writes it in place
+//   eps   [B][R][P][Kp]  standard normals, plane-major: one warp reads 32 consecutive samples of one (t,u)
+//                        plane (128 B coalesced); Kp = K rounded up to 4 (float4 stores of the generator).
+//                        B = eps_buffers: 2 when the next solve's normals are generated beside the current solve
+//                        (noise prefetch); solve n uses buffer n & (B-1), n = the device-side solve counter
 //   cost     [R][K]      per-sample cost;  weight [R][K] exp(-(c - c_min)/lambda)
-//   cmin     [R]         ordered-uint encoding of the minimum cost (atomicMin target)
+//   cmin     [R]         ordered-uint encoding of the minimum cost (atomicMin target of K2); re-armed (all ones) by
+//                        the last kernel of a solve that reads it, i.e. by the tail
 //   wpart    [R][NB3][2] per-block partial (sum w, sum w^2) of the weight kernel (fixed-order final sum)
 //   npart    [R][P][NC]  per-chunk partial numerators of the weighted control reduction
 //   record   [R][REC]    REC = 4 + P floats: {c_min, sum w, sum w^2, -, N[P]} -- the exchanged partial
@@ -56,6 +67,10 @@ struct DeviceState {
   SolveHeader *hdr = nullptr;
   float *window = nullptr, *state = nullptr, *nominal = nullptr;
   float *eps = nullptr, *cost = nullptr, *weight = nullptr, *wpart = nullptr, *npart = nullptr;
+  int eps_buffers = 1;        // 1 or 2 (noise prefetch); buffer of solve n = n & (eps_buffers - 1)
+  size_t eps_buf_elems = 0;   // R * planes * Kp
+  bool feedback = true;       // the merge writes the new controls into `nominal` (warm start of the next solve)
+  long long xchg_timeout_cycles = 4000000000ll;  // peer exchange: device-side wait limit of the merge
   float *record = nullptr, *gathered = nullptr;
   float *u_new = nullptr, *stats = nullptr;
   unsigned int *cmin = nullptr;
@@ -79,27 +94,36 @@ struct DeviceState {
   float grid_h_min = 0.05f;   // K = 2^20: flat below 0.05 (0.025 .. 0.10 tried); small handles are bound by max_cells
   float grid_margin = 0.f;    // > 0: absolute margin around the window's bounding box; else a quarter of the horizon reach
   int grid_lanes = 0;         // > 0: lanes per cell of K0 (tuning); else chosen by the handle's total cell count
-  // K2 noise ring: 1 = per-warp TMA tiles of the noise tensor (needs eps_map), 0 = per-thread cp.async
-  bool fuse_controls = false;  // K2 (TMA ring) also produces the weighted-control records (many-robot handles); false: K3 + K4
+  bool fuse_controls = false;  // K2 also produces the weighted-control records of its CTAs; false: K3 + K4
   float *cta_part = nullptr;  // [R][ceil(K/128)][rec_stride] per-CTA records {m, S, Q, -, N[P]} of the fused K2
-  int k2_ring = 1;
   int k4_groups = 0;  // > 0: plane groups per K4 block (tuning); else by the number of blocks
+  unsigned int *tail_ticket = nullptr;  // [R + 1] "last block" tickets of the one-kernel tail (fused-controls path)
+  int side_carveout = -1;     // shared-memory carve-out (per cent) given to the side-stream kernels: K2's own
+  ControlBounds bounds = {};  // kernel parameter of K2 (kept equal to hdr->P.u_min / u_max by the host)
   bool eps_map_valid = false;
-  CUtensorMap eps_map;  // 2-D {Kp, R * planes} f32, box {32, 4 * U}
+  CUtensorMap eps_map;  // 2-D {Kp, eps_buffers * R * planes} f32, box {32, 4 * U}
 };
 
+// Preferred L1 / shared-memory split of a kernel, in per cent of the maximum shared memory (< 0: leave the default).
+// Two kernels with different carve-outs are never resident on one SM at the same time, so the side stream's kernels
+// (candidate grid, noise prefetch) are given K2's split (DeviceState::side_carveout) -- otherwise they run before or
+// after K2 instead of beside it.  Remembers the last value per device and function.
+cudaError_t set_carveout(const void *kernel, int percent);
+// the split the driver picks for the K2 instantiation of this handle (mppi_rollout_pruned.cu)
+int rollout_carveout_percent(const DeviceState &d);
+
 constexpr int kHeaderBytes = 256;
+constexpr int kStateStride = 4;     // floats per robot of the state record {yaw, roll, pitch, -} (x = y = 0: robot frame)
 constexpr int kExchangeHeaderBytes = 256;  // flags[2][G] (G <= 32) at the start of an exchange buffer
 constexpr int kWeightBlock = 256;   // threads of the weight kernel, 4 samples per thread
 constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
 constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
-constexpr int kRescaleMaxCtas = 128;  // CTA records folded by one block of cta_rescale_kernel
+constexpr int kRescaleMaxCtas = 128;  // most CTA records folded by one block of rescale_tail_kernel
 static_assert(sizeof(SolveHeader) <= kHeaderBytes, "SolveHeader must fit its slot");
+static_assert(kRescaleMaxCtas % 16 == 0, "the tail reads the records sixteen at a time");
 
-// K1  Philox4x32-10 + Box-Muller -> eps (float4 stores).  Also resets cmin.
-cudaError_t launch_noise(const DeviceState &d, cudaStream_t s);
-// used instead of K1 when the caller supplied the noise tensor (mppi_set_noise)
-cudaError_t launch_reset_cmin(const DeviceState &d, cudaStream_t s);
+// K1  Philox4x32-10 + Box-Muller -> eps (float4 stores) of solve (counter + ahead), into that solve's buffer.
+cudaError_t launch_noise(const DeviceState &d, int ahead, cudaStream_t s);
 // K2  fused rollout + cost (+ block min -> atomicMin on cmin).  scan_mode: 1 literal, 2 pruned.
 cudaError_t launch_rollout_cost(const DeviceState &d, int scan_mode, bool write_nearest, bool write_states, bool fused,
                                 cudaStream_t s);
@@ -108,16 +132,19 @@ cudaError_t launch_window_builder(const DeviceState &d, cudaStream_t s);
 // K0  candidate grid of the pruned scan, once per robot and solve (mppi_rollout_pruned.cu)
 cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s);
 // K2 production variant (mppi_rollout_pruned.cu): exact pruned nearest-point scan, bit-identical costs
-// fused: the CTAs also write their weighted-control records into d.cta_part (TMA ring only); launch_cta_rescale then
-// replaces K3 + K4 and fills wpart / npart with cta_rescale_groups(n_cta) partials per robot and plane
-cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, cudaStream_t s);
-cudaError_t launch_cta_rescale(const DeviceState &d, cudaStream_t s);
-int cta_rescale_groups(int n_cta);
+// fused: the CTAs also write their weighted-control records into d.cta_part; launch_rescale_tail then replaces
+// K3 + K4 + K5 + K6.  write_nearest: the instantiation that records the argmin index (MPPI_DEBUG_NEAREST)
+cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, bool write_nearest, cudaStream_t s);
+// The whole tail of the fused-controls path in ONE launch: rescale of the per-CTA records, fixed-order final sums,
+// then (last block) the record exchange with the peers over NVLink (p2p) or the local merge -> u_new, warm start,
+// stats, counter++.  mode: 0 = unsharded, 1 = peer exchange, 2 = record only (NCCL all-gather + merge follow).
+cudaError_t launch_rescale_tail(const DeviceState &d, int mode, cudaStream_t s);
 bool pruned_scan_supported(int T, int planes);
 // tensor map of d.eps for K2's TMA ring (after d.eps, Kp, R, planes, U are final)
 cudaError_t make_eps_tensor_map(DeviceState &d);
-// K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums
-cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
+// K3  weights w = exp(-(c - c_min)/lambda), per-block partial sums.  after_solve: the on-demand debug tap (c_min from
+// the record; the tail of the solve has re-armed cmin by then)
+cudaError_t launch_weights(const DeviceState &d, bool after_solve, cudaStream_t s);
 // planes per block of K4 (1, 2 or 4) and the matching number of sample chunks: nchunk = ceil(Kp / (4096 / ppb))
 int reduce_planes_per_block(int Kp);
 // K4  weighted control reduction partials; fuse_weights: K3 folded in (small K; then nb3 must equal nchunk)
@@ -126,9 +153,18 @@ cudaError_t launch_weighted_controls(const DeviceState &d, bool fuse_weights, cu
 cudaError_t launch_finalize(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge(const DeviceState &d, cudaStream_t s);
 // C1 over NVLink peer memory instead of NCCL: K5 whose last block pushes the record into every peer's exchange
-// buffer, and K6 that waits for the peers' flags (one process per GPU, buffers shared through CUDA IPC)
-cudaError_t launch_finalize_push(const DeviceState &d, cudaStream_t s);
-cudaError_t launch_merge_wait(const DeviceState &d, cudaStream_t s);
+// buffer, waits for the peers' flags and merges (one process per GPU, buffers shared through CUDA IPC)
+cudaError_t launch_finalize_exchange(const DeviceState &d, cudaStream_t s);
+// what the exchanging block needs (kernel argument)
+struct ExchangeArgs {
+  void *const *peers;     // [G] exchange-buffer base pointers of all ranks (own one included)
+  void *xbuf;             // this rank's exchange buffer
+  unsigned int *seq;      // solve sequence number of the exchange (parity selects the slot set)
+  unsigned int *ticket;   // "last block" ticket
+  int rank, G;
+  long long timeout_cycles;
+};
+ExchangeArgs exchange_args(const DeviceState &d);
 // K5 + K6 in one launch when the handle is not sharded (identical results)
 cudaError_t launch_finalize_merge(const DeviceState &d, cudaStream_t s);
 

@@ -25,10 +25,11 @@
 //
 // Kernels in this file:
 //   candidate_grid_kernel<LANES>     K0
-//   rollout_cost_tma_kernel<MODEL>   K2, production: the normals arrive through a per-warp TMA ring; for many-robot
-//                                    handles the CTA also reduces its weighted controls (cta_weighted_controls)
-//   rollout_cost_pruned_kernel<MODEL> K2 with a per-thread cp.async ring (MPPI_K2_RING=0; same bits)
-//   cta_rescale_kernel               K3': per-CTA records -> partial sums at the robot's global minimum
+//   rollout_cost_tma_kernel<MODEL,TAP> K2, production: the normals arrive through a per-warp TMA ring; optionally the
+//                                    CTA also reduces its weighted controls (cta_weighted_controls).  TAP = the
+//                                    instantiation that also records the argmin index (MPPI_DEBUG_NEAREST)
+//   rescale_tail_kernel              K3' (per-CTA records -> partial sums at the robot's global minimum) + K5 + K6
+//                                    (+ the NVLink record exchange) in one launch
 #include <cuda.h>
 
 #include "mppi_device.cuh"
@@ -120,6 +121,35 @@ __device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float 
   return best;
 }
 
+// The same scan, also returning the FIRST index that attains the minimum (-1 when no point is closer than the cap):
+// what the literal loop `if (d2 < best) { best = d2; arg = j; }` (DD:186-190) records.  Every point that can be
+// nearest -- ties included -- lies inside the candidate range (points outside are strictly farther), the range is
+// scanned in index order, and the padding pairs repeat point T-1 AFTER it, so a strict `<` finds the same index.
+__device__ __forceinline__ float scan_pairs_arg(unsigned pairs_s, uint32_t e, float x, float y, int *arg) {
+  const u64 xx = pack2(x, x), yy = pack2(y, y);
+  unsigned p = pairs_s + (e & 0xFFFFu);
+  const unsigned p_end = p + (e >> 16);
+  float best = kDist2Cap;
+  int bi = -1;
+#pragma unroll 1
+  do {
+    const float4 a = lds128(p), b = lds128(p + 16u);
+    float d[4];
+    unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), d[0], d[1]);
+    unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), d[2], d[3]);
+    const int j0 = (int)((p - pairs_s) >> 3);  // 16 bytes per pair of points
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (d[k] < best) {
+        best = d[k];
+        bi = j0 + k;
+      }
+    p += 32u;
+  } while (p != p_end);
+  *arg = bi;
+  return best;
+}
+
 struct GridView {
   const uint32_t *cells;  // [ny + 2][nx + 2] cell entries; the one-cell border ring says "scan the whole window"
                           // (positions outside the grid are clamped to it)
@@ -144,29 +174,6 @@ __device__ __forceinline__ uint32_t grid_cell(const GridView &g, u64 xy) {
   const int iy = clamp0(__float2int_rd(fy), g.iymax);
   return __ldg(g.cells + (iy * g.nx2 + ix));
 }
-// Exact min_j min(d2(p, r_j), 1e4) over the whole window, given the cell entry of (x, y).
-__device__ __forceinline__ float min_dist2_cell(uint32_t e, unsigned pairs_s, float x, float y) {
-  return scan_pairs(pairs_s, e, x, y);
-}
-
-// 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, so the normals of future control
-// steps stream in behind the arithmetic without ever blocking a register scoreboard
-__device__ __forceinline__ void cp_async_f32(unsigned smem_dst, const void *gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-constexpr int kRing = 4;  // ring of control steps in flight per thread (prefetch distance: two iterations)
-
-template <int J>
-struct SlotC {
-  static constexpr int value = J;
-};
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(128)
     if (sub == 0) cells[(size_t)robot * max_cells + cell] = cell_entry(0, ((T + 1) / 2 + 1) / 2);
     return;
   }
-  const unsigned quad = (kCellLanes == 32 ? 0xffffffffu : ((1u << kCellLanes) - 1u))
+  const unsigned quad = (kCellLanes >= 32 ? 0xffffffffu : ((1u << (kCellLanes & 31)) - 1u))
                         << ((threadIdx.x & 31) / kCellLanes * kCellLanes);
   const int ix = tx - 1, iy = ty - 1;
   const float ccx = gh.x0 + ((float)ix + 0.5f) * gh.h, ccy = gh.y0 + ((float)iy + 0.5f) * gh.h;
@@ -332,6 +339,8 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
   if (d.grid_lanes > 0) lanes = d.grid_lanes;
 #define MPPI_LAUNCH_K0(L)                                                                                        \
   do {                                                                                                           \
+    cudaError_t ce = set_carveout((const void *)candidate_grid_kernel<L>, d.side_carveout);                      \
+    if (ce != cudaSuccess) return ce;                                                                            \
     if (smem > 48 * 1024) {                                                                                      \
       cudaError_t e = cudaFuncSetAttribute(candidate_grid_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem);                                                           \
@@ -342,6 +351,8 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
                                                      d.grid_max_cells, d.grid_h_min, d.grid_margin);             \
   } while (0)
   switch (lanes) {
+    case 32: MPPI_LAUNCH_K0(32); break;
+    case 16: MPPI_LAUNCH_K0(16); break;
     case 8: MPPI_LAUNCH_K0(8); break;
     case 4: MPPI_LAUNCH_K0(4); break;
     case 2: MPPI_LAUNCH_K0(2); break;
@@ -354,27 +365,24 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------
 // K2 (pruned)
 // ---------------------------------------------------------------------------------------------------------
-size_t pruned_smem_bytes(int T, int planes, int U) {
-  // window pairs {x0,x1,y0,y1} x (ceil(T/2) + 1 pad) | ring of normals [kRing][U][128] | nominal padded by two steps
-  return sizeof(float4) * (size_t)((T + 1) / 2 + 1) + sizeof(float) * ((size_t)kRing * U * 128 + (size_t)planes + 2 * U);
-}
-
 // What one thread needs besides its sample index (all CTA-uniform)
 struct ThreadCtx {
   const SolveParams *sP;    // shared copy of the per-solve constants
+  const ControlBounds *kb;  // clamp bounds: kernel parameter (constant bank operands, no registers)
   GridView gv;
-  unsigned pairs_s, ring_s, nom_s;  // shared-window addresses: window pairs, this thread's ring column, warm start
-  const float *e_ptr;       // normals of (step 0, control 0) of this sample (cp.async ring only)
-  const float *st;          // state record of the robot
-  size_t Kp;
+  unsigned pairs_s, nom_s;  // shared-window addresses: window pairs, warm start
+  float state0[5];          // {0, 0, yaw, roll, pitch}: the robot's state in its own frame
+  int *tap_row;             // TAP only: nearest[sample][0..T) of this thread's sample (nullptr past K)
   int T;
 };
 
 // Registers of one rollout: pose, carried cos/sin pairs, cost accumulators, the candidate range of the current state.
-template <int MODEL, bool SMALL>
+// TAP: the debug instantiation that also records the argmin index of every cost state (MPPI_DEBUG_NEAREST).
+template <int MODEL, bool SMALL, bool TAP>
 struct Rollout {
   static constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   const SolveParams &sP;
+  const ControlBounds &kb;
   const GridView &gv;
   const unsigned pairs_s, nom_s;
   u64 xy;  // position {x, y} as one f32x2 register pair
@@ -383,21 +391,19 @@ struct Rollout {
   uint32_t cell;
   float sigma, dt, v_ref;
   bool steer_off;
-  float lo[U], hi[U];
+  int *tap_row;
+  int tap_t;
 
   __device__ __forceinline__ Rollout(const ThreadCtx &cx)
-      : sP(*cx.sP), gv(cx.gv), pairs_s(cx.pairs_s), nom_s(cx.nom_s) {
-    xy = pack2(cx.st[0], cx.st[1]);
-    att.init(cx.st);
+      : sP(*cx.sP), kb(*cx.kb), gv(cx.gv), pairs_s(cx.pairs_s), nom_s(cx.nom_s) {
+    xy = pack2(cx.state0[0], cx.state0[1]);
+    att.init(cx.state0);
     sigma = sP.sigma;
     dt = sP.dt;
     v_ref = sP.v_ref;
     steer_off = MODEL == kFullBody && sP.steer_off;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      lo[u] = sP.u_min[u];
-      hi[u] = sP.u_max[u];
-    }
+    tap_row = cx.tap_row;
+    tap_t = 0;
     cell = grid_cell(gv, xy);
   }
   // sampling (D5) of step t: normals at shared address src + u * row_bytes; past the last step the result is never
@@ -414,8 +420,17 @@ struct Rollout {
     }
     if (U & 1) raw[U - 1] = fmaf(lds32_volatile(src + (U - 1) * row_bytes), sigma, lds32(nom + (U - 1) * 4u));
 #pragma unroll
-    for (int u = 0; u < U; ++u) dst[u] = clamp_ref(raw[u], lo[u], hi[u]);
+    for (int u = 0; u < U; ++u) dst[u] = clamp_ref(raw[u], kb.lo[u], kb.hi[u]);
     if (steer_off) dst[2] = 0.f;  // FB:517
+  }
+  // min_j min(d2, 1e4) of the current state over its cell's candidate range (+ the argmin for the debug tap)
+  __device__ __forceinline__ float nearest_d2(float x, float y) {
+    if (!TAP) return scan_pairs(pairs_s, cell, x, y);
+    int arg;
+    const float d2 = scan_pairs_arg(pairs_s, cell, x, y, &arg);
+    if (tap_row) tap_row[tap_t] = arg;
+    ++tap_t;
+    return d2;
   }
   // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
   // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
@@ -431,7 +446,7 @@ struct Rollout {
     xy = fma2(mul2(pack2(cur[0], cur[0]), pack2(ch, sh)), pack2(dt, dt), xy);
     step_attitude<MODEL, SMALL>(att, cur, dt);
     const uint32_t cell_next = grid_cell(gv, xy);
-    acc.path += min_dist2_cell(cell, pairs_s, x0, y0);
+    acc.path += nearest_d2(x0, y0);
     cell = cell_next;
     const float dv = cur[0] - v_ref;
     acc.vel = fmaf(dv, dv, acc.vel);
@@ -448,7 +463,7 @@ struct Rollout {
     if (MODEL != kFullBody) {  // state T-1: path term only (D1)
       float x, y;
       unpack2(xy, x, y);
-      acc.path += min_dist2_cell(cell, pairs_s, x, y);
+      acc.path += nearest_d2(x, y);
     }
     float yaw0_err = 0.f;
     if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
@@ -459,80 +474,13 @@ struct Rollout {
   }
 };
 
-// The rollout of one sample, normals streamed by the per-thread cp.async ring.
-// SMALL = angles_are_small(): the instantiation without the per-step angle range tests.
-template <int MODEL, bool SMALL>
-__device__ __forceinline__ float rollout_thread(const ThreadCtx &cx) {
-  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
-  constexpr unsigned kSlotBytes = U * 128 * 4;
-  Rollout<MODEL, SMALL> r(cx);
-  const unsigned ring_s = cx.ring_s;
-  const int T = cx.T;
-  const int steps = T - 1;
-  // iterations that accumulate cost and advance the state: t < T-1 (DD/SD) or t < T-2 (FB, whose cost never
-  // looks at the last two states, FB:409)
-  const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
-  float ca[U], cb[U];  // controls of the current and the next step (roles alternate, no register moves)
-  // normals of control step t: eps[(t*U + u)*Kp + i], streamed through this thread's column of the ring
-  const size_t Kp = cx.Kp;
-  const size_t step_stride = (size_t)U * Kp;
-  const float *e_ptr = cx.e_ptr;
-  // start the copy of step t into ring slot `slot` (nothing past the last step); one commit group per step
-  auto issue = [&](int t, unsigned slot) {
-    if (t < steps) {
-      const unsigned dst = ring_s + slot * kSlotBytes;
-#pragma unroll
-      for (int u = 0; u < U; ++u) cp_async_f32(dst + u * 512u, e_ptr + (size_t)u * Kp);
-      e_ptr += step_stride;
-    }
-    cp_async_commit();
-  };
-  auto make = [&](int t, unsigned slot, float *dst) { r.make(t, ring_s + slot * kSlotBytes, 512u, dst); };
-#pragma unroll
-  for (int k = 0; k < kRing; ++k) issue(k, (unsigned)k);
-  cp_async_wait<kRing - 2>();  // steps 0 and 1 have landed
-  make(0, 0u, ca);
-  make(1, 1u, cb);
-  // Iteration t consumes step t (cur) and t+1 (nxt), then refills: step t+4 goes into slot t%4 (held step t,
-  // consumed), step t+2 -- issued two iterations ago -- is sampled from slot (t+2)%4 into the register set that
-  // held step t.  Unrolled by the ring size so that slots and register roles are compile-time constants.
-  int t = 0;
-  for (; t + kRing <= n_iter; t += kRing) {
-    r.advance(ca, cb);
-    issue(t + 4, 0u);
-    cp_async_wait<2>();
-    make(t + 2, 2u, ca);
-    r.advance(cb, ca);
-    issue(t + 5, 1u);
-    cp_async_wait<2>();
-    make(t + 3, 3u, cb);
-    r.advance(ca, cb);
-    issue(t + 6, 2u);
-    cp_async_wait<2>();
-    make(t + 4, 0u, ca);
-    r.advance(cb, ca);
-    issue(t + 7, 3u);
-    cp_async_wait<2>();
-    make(t + 5, 1u, cb);
-  }
-  for (; t < n_iter; ++t) {  // at most kRing - 1 iterations; (ca, cb) = (step t, step t+1) on entry
-    r.advance(ca, cb);
-    issue(t + 4, (unsigned)(t & 3));
-    cp_async_wait<2>();
-#pragma unroll
-    for (int u = 0; u < U; ++u) ca[u] = cb[u];
-    make(t + 2, (unsigned)((t + 2) & 3), cb);
-  }
-  return r.finish(cx.st);
-}
-
 // ---- TMA ring -------------------------------------------------------------------------------------------------
 // One ring PER WARP: a stage is the tile {32 samples of the warp} x {kStageSteps control steps x U planes} of the
-// plane-major noise tensor, fetched by ONE cp.async.bulk.tensor issued by lane 0 and landing as [row][32] floats
-// (128 B rows, conflict-free column reads).  Completion is signalled on the stage's mbarrier (expect-tx bytes);
-// a slot is refilled after __syncwarp(), once every lane has consumed its column in an Euler step.  Warps never
-// wait for each other.  Per control step this costs ~2 issue slots instead of the ~14 of the per-thread LDGSTS
-// ring (address arithmetic, predicates, commit / wait groups).
+// plane-major noise tensor, fetched by ONE cp.async.bulk.tensor issued by an elected lane and landing as [row][32]
+// floats (128 B rows, conflict-free column reads).  Completion is signalled on the stage's mbarrier (expect-tx
+// bytes); a slot is refilled after __syncwarp(), once every lane has consumed its column in an Euler step.  Warps
+// never wait for each other.  Per control step this costs ~2 issue slots (a per-thread LDGSTS ring -- address
+// arithmetic, predicates, commit / wait groups -- cost ~14 and was dropped).
 constexpr int kStageSteps = 4;
 constexpr int kStages = 3;
 
@@ -580,16 +528,16 @@ struct TmaCtx {
   unsigned ring_s;  // this warp's ring: kStages tiles of kStageSteps * U rows x 128 B
   unsigned bar_s;   // this warp's kStages mbarriers
   int c0;           // first sample of the warp
-  int row0;         // robot * planes
+  int row0;         // first row of this robot's planes in the (double-buffered) tensor
 };
 
-template <int MODEL, bool SMALL>
+template <int MODEL, bool SMALL, bool TAP>
 __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const TmaCtx &tc) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   constexpr int kRows = kStageSteps * U;
   constexpr unsigned kTileBytes = kRows * 128u;
   constexpr unsigned kStepBytes = U * 128u;
-  Rollout<MODEL, SMALL> r(cx);
+  Rollout<MODEL, SMALL, TAP> r(cx);
   const int T = cx.T;
   const int n_iter = MODEL == kFullBody ? T - 2 : T - 1;
   // tiles 0 .. n_tiles-1 cover control steps 0 .. n_iter (the last one may lie past the end: sampled, never used;
@@ -645,73 +593,15 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
       for (int u = 0; u < U; ++u) ca[u] = cb[u];
     }
   }
-  return r.finish(cx.st);
+  return r.finish(cx.state0);
 }
 
-#ifndef MPPI_K2_MINBLOCKS
-#define MPPI_K2_MINBLOCKS 1
-#endif
-template <int MODEL>
-__global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
-    rollout_cost_pruned_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ eps,
-                               const float *__restrict__ nominal, const float *__restrict__ window,
-                               const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
-                               const uint32_t *__restrict__ cells, float *__restrict__ cost,
-                               unsigned int *__restrict__ cmin, int K, int Kp, int planes, int win_stride, int T,
-                               int max_cells) {
-  constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ SolveParams sP;
-  __shared__ float s_red[32];
-  __shared__ GridHeader s_gh;
-  const int robot = blockIdx.y;
-  const int NP = (T + 1) / 2;
-  float4 *s_pairs = reinterpret_cast<float4 *>(smem_raw);
-  float *s_eps = reinterpret_cast<float *>(s_pairs + NP + 1);
-  float *s_nom = s_eps + kRing * U * 128;
-
-  const float *g_win = window + (size_t)robot * win_stride;
-  load_params_to_shared(&sP, hdr);
-  if (threadIdx.x == 0) s_gh = ghdr[robot];
-  for (int q = threadIdx.x; q < NP + 1; q += blockDim.x) {
-    // odd T and the pad pair: the last point again (no effect on a minimum)
-    const int j0 = min(2 * q, T - 1), j1 = min(2 * q + 1, T - 1);
-    s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
-  }
-  for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
-    s_nom[j] = j < planes ? nominal[(size_t)robot * planes + j] : 0.f;
-  __syncthreads();
-
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float c = 0.f;
-  if (i < K) {
-    const uint32_t *cp = cells + (size_t)robot * max_cells;
-    asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
-    ThreadCtx cx;
-    cx.sP = &sP;
-    cx.gv = GridView{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.nx + 1, s_gh.ny + 1};
-    cx.pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
-    cx.ring_s = (unsigned)__cvta_generic_to_shared(s_eps + threadIdx.x);
-    cx.nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
-    // pin the three shared-window addresses in registers (otherwise they are re-derived from SR_CgaCtaId per step)
-    asm volatile("" : "+r"(cx.pairs_s), "+r"(cx.ring_s), "+r"(cx.nom_s));
-    cx.e_ptr = eps + (size_t)robot * planes * Kp + i;
-    cx.st = state + (size_t)robot * 8;
-    cx.Kp = (size_t)Kp;
-    cx.T = T;
-    // CTA-uniform choice of the instantiation (per-solve constants: dt and the control bounds)
-    c = angles_are_small(sP) ? rollout_thread<MODEL, true>(cx) : rollout_thread<MODEL, false>(cx);
-    cost[(size_t)robot * K + i] = c;
-  }
-  block_min_to_global(c, i < K, cmin + robot, s_red);
-}
-
-// ---- fused weighted-control partials of one CTA's 128 samples (replaces K3 + K4 on the production path) -------
+// ---- fused weighted-control partials of one CTA's 128 samples (replaces K3 + K4) -------------------------------
 // calc_Weights (DD:216-222) + determine_OptimalSolution (DD:228-236) against the CTA's own minimum m_cta:
 //   w_i = exp(-(c_i - m_cta)/lambda),  S = sum w,  Q = sum w^2,  N[p] = sum_i w_i * clamp(u*_p + sigma*eps[p][i])
-// written as the record {m_cta, S, Q, -, N[planes]}; cta_rescale_kernel brings the records of all CTAs to the
-// robot's global minimum (the same log-sum-exp merge as between GPUs, section 6 of DESIGN.md).  The CTA re-reads
-// its 128 x planes tile of the normals right after streaming it through the TMA ring -- mostly from L2, and in the
+// written as the record {m_cta, S, Q, -, N[planes]}; the rescale brings the records of all CTAs to the robot's
+// global minimum (the same log-sum-exp merge as between GPUs, section 6 of DESIGN.md).  The CTA re-reads its
+// 128 x planes tile of the normals right after streaming it through the TMA ring -- mostly from L2, and in the
 // shadow of the other CTAs' rollouts (K2 uses a quarter of the HBM bandwidth) -- instead of a separate pass of
 // the whole tensor through HBM.  Not inlined (called once per thread, keeps the rollout loop's code compact).
 template <int MODEL>
@@ -785,22 +675,28 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float 
   }
 }
 
-// K2 with the TMA ring.  Same prologue as above; dynamic shared memory = ring [4 warps][kStages][rows][32] (1 KB
-// aligned) | window pairs | warm start.  Whole warps run the rollout (the refill needs all 32 lanes at the
-// __syncwarp); lanes past K compute on zero / padding normals and are masked at the store.
+// K2 with the TMA ring.  Dynamic shared memory = ring [4 warps][kStages][rows][32] (1 KB aligned) | window pairs |
+// warm start.  Whole warps run the rollout (the refill needs all 32 lanes at the __syncwarp); lanes past K compute
+// on zero / padding normals and are masked at the store.
 size_t pruned_tma_smem_bytes(int T, int planes, int U) {
   return (size_t)4 * kStages * kStageSteps * U * 128 + sizeof(float4) * (size_t)((T + 1) / 2 + 1) +
          sizeof(float) * ((size_t)planes + 2 * U);
 }
 
-template <int MODEL>
+#ifndef MPPI_K2_MINBLOCKS
+#define MPPI_K2_MINBLOCKS 1
+#endif
+template <int MODEL, bool TAP>
 __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
-    rollout_cost_tma_kernel(const __grid_constant__ CUtensorMap eps_map, const SolveHeader *__restrict__ hdr,
+    rollout_cost_tma_kernel(const __grid_constant__ CUtensorMap eps_map, const __grid_constant__ ControlBounds kb,
+                            const SolveHeader *__restrict__ hdr,
                             const float *__restrict__ nominal, const float *__restrict__ window,
                             const float *__restrict__ state, const GridHeader *__restrict__ ghdr,
                             const uint32_t *__restrict__ cells, float *__restrict__ cost,
                             unsigned int *__restrict__ cmin, int K, int planes, int win_stride, int T, int max_cells,
-                            const float *__restrict__ eps, int Kp, float *__restrict__ cta_part, int part_stride) {
+                            const float *__restrict__ eps, int Kp, float *__restrict__ cta_part, int part_stride,
+                            const uint32_t *__restrict__ counter, uint32_t pmask, size_t buf_elems,
+                            int *__restrict__ nearest) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   constexpr int kWarpRingBytes = kStages * kStageSteps * U * 128;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -819,6 +715,7 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
   if (threadIdx.x < 4 * kStages) mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[threadIdx.x]), 1u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int q = threadIdx.x; q < NP + 1; q += blockDim.x) {
+    // odd T and the pad pair: the last point again (no effect on a minimum)
     const int j0 = min(2 * q, T - 1), j1 = min(2 * q + 1, T - 1);
     s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
   }
@@ -830,81 +727,209 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
   // warp index through a shuffle: the compiler then knows it is warp-uniform (TMA operands live in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int warp_first = blockIdx.x * blockDim.x + warp * 32;
+  const uint32_t par = eps_parity(counter, pmask);  // which buffer of the noise tensor belongs to this solve
   float c = 0.f;
   if (warp_first < K) {  // warp-uniform
     const uint32_t *cp = cells + (size_t)robot * max_cells;
     asm volatile("" : "+l"(cp));  // keep the robot's table base in a register pair (no per-step recomputation)
     ThreadCtx cx;
     cx.sP = &sP;
+    cx.kb = &kb;
     cx.gv = GridView{cp, s_gh.inv_h, s_gh.cx, s_gh.cy, s_gh.nx + 2, s_gh.nx + 1, s_gh.ny + 1};
     cx.pairs_s = (unsigned)__cvta_generic_to_shared(s_pairs);
     cx.nom_s = (unsigned)__cvta_generic_to_shared(s_nom);
-    cx.ring_s = 0;
-    cx.e_ptr = nullptr;
-    cx.st = state + (size_t)robot * 8;
-    cx.Kp = 0;
+    {
+      const float *st = state + (size_t)robot * kStateStride;  // {yaw, roll, pitch, -}
+      cx.state0[0] = cx.state0[1] = 0.f;
+      cx.state0[2] = st[0];
+      cx.state0[3] = st[1];
+      cx.state0[4] = st[2];
+    }
+    cx.tap_row = (TAP && i < K) ? nearest + ((size_t)robot * K + i) * T : nullptr;
     cx.T = T;
     TmaCtx tc;
     tc.map = &eps_map;
     tc.ring_s = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(warp * kWarpRingBytes);
     tc.bar_s = (unsigned)__cvta_generic_to_shared(&s_bar[warp * kStages]);
     tc.c0 = warp_first;
-    tc.row0 = robot * planes;
+    tc.row0 = ((int)par * (int)gridDim.y + robot) * planes;
     asm volatile("" : "+r"(cx.pairs_s), "+r"(cx.nom_s), "+r"(tc.ring_s), "+r"(tc.bar_s));
-    c = angles_are_small(sP) ? rollout_thread_tma<MODEL, true>(cx, tc) : rollout_thread_tma<MODEL, false>(cx, tc);
+    c = angles_are_small(sP) ? rollout_thread_tma<MODEL, true, TAP>(cx, tc) : rollout_thread_tma<MODEL, false, TAP>(cx, tc);
     if (i < K) cost[(size_t)robot * K + i] = c;
   }
   const float m_cta = block_min_to_global(c, i < K, cmin + robot, s_red);
   if (cta_part == nullptr) return;  // kernel argument: uniform
-  cta_weighted_controls<MODEL>(sP, hdr->inv_lambda, c, i < K, m_cta, s_nom, eps + (size_t)robot * planes * Kp, Kp, planes,
+  cta_weighted_controls<MODEL>(sP, hdr->inv_lambda, c, i < K, m_cta, s_nom,
+                               eps + (size_t)par * buf_elems + (size_t)robot * planes * Kp, Kp, planes,
                                cta_part + ((size_t)robot * gridDim.x + blockIdx.x) * part_stride);
 }
 
-// K3': brings the per-CTA records of K2 to the robot's global minimum and folds them into the partial arrays the
-// finalize kernels already sum:  a_c = exp(-(m_c - c_min)/lambda);  wpart[g] = {sum_c a_c S_c, sum_c a_c^2 Q_c},
-// npart[p][g] = sum_c a_c N_c[p]  over the CTAs c of group g (fixed order).  grid = (groups, robots).
-__global__ void __launch_bounds__(256)
-    cta_rescale_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
-                       const unsigned int *__restrict__ cmin, float *__restrict__ wpart, float *__restrict__ npart,
-                       int planes, int n_cta, int part_stride, int groups) {
-  __shared__ float s_a[kRescaleMaxCtas];
-  const int robot = blockIdx.y, g = blockIdx.x;
-  const int per = (n_cta + groups - 1) / groups;  // <= kRescaleMaxCtas (launch_cta_rescale)
-  const int c0 = g * per, c1 = min(c0 + per, n_cta);
+// ---- K3': rescale of the per-CTA records ------------------------------------------------------------------------
+// Brings the records of K2's CTAs to the robot's global minimum and folds them into partial sums:
+//   a_c = exp(-(m_c - c_min)/lambda);  wpart[g] = {sum_c a_c S_c, sum_c a_c^2 Q_c},  npart[g][p] = sum_c a_c N_c[p]
+// over the CTAs c of group g.  One block per (group, robot); thread = plane (coalesced over the records' rows),
+// sixteen independent accumulators per thread keep sixteen loads in flight (the tail is a chain of L2 round trips, not
+// bandwidth) and are combined in a fixed order (deterministic).
+constexpr int kTailMlp = 16;
+__device__ __forceinline__ float sum_fixed(const float (&a)[kTailMlp]) {
+  float s[kTailMlp / 2];
+#pragma unroll
+  for (int k = 0; k < kTailMlp / 2; ++k) s[k] = a[2 * k] + a[2 * k + 1];
+#pragma unroll
+  for (int w = kTailMlp / 4; w > 0; w >>= 1)
+#pragma unroll
+    for (int k = 0; k < w; ++k) s[k] = s[2 * k] + s[2 * k + 1];
+  return s[0];
+}
+__device__ __forceinline__ void rescale_group(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
+                                              const unsigned int *__restrict__ cmin, float *__restrict__ wpart,
+                                              float *__restrict__ npart, int planes, int n_cta, int part_stride,
+                                              int groups, int per, int robot, int g, float *s_a) {
+  const int c0 = g * per, c1 = min(c0 + per, n_cta), nc = c1 - c0;
   const float c_min = ordered_to_float(cmin[robot]);
   const float inv_lambda = hdr->inv_lambda;
-  const float *part = cta_part + (size_t)robot * n_cta * part_stride;
-  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
-    s_a[c - c0] = expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda);
+  const float *part = cta_part + ((size_t)robot * n_cta + c0) * part_stride;
+  for (int c = threadIdx.x; c < kRescaleMaxCtas; c += blockDim.x)  // padded with zeros: no tail code below
+    s_a[c] = c < nc ? expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda) : 0.f;
   __syncthreads();
+  const int ncm = (nc + kTailMlp - 1) / kTailMlp * kTailMlp;  // <= kRescaleMaxCtas (a multiple of kTailMlp)
   for (int p = threadIdx.x; p < planes; p += blockDim.x) {
-    float n = 0.f;
-    for (int c = c0; c < c1; ++c) n = fmaf(s_a[c - c0], part[(size_t)c * part_stride + 4 + p], n);
-    npart[((size_t)robot * planes + p) * groups + g] = n;
+    float acc[kTailMlp];
+#pragma unroll
+    for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
+    for (int c = 0; c < ncm; c += kTailMlp) {
+      float v[kTailMlp];
+#pragma unroll
+      for (int k = 0; k < kTailMlp; ++k)
+        v[k] = part[(size_t)min(c + k, nc - 1) * part_stride + 4 + p];  // weight 0 past the end
+#pragma unroll
+      for (int k = 0; k < kTailMlp; ++k) acc[k] = fmaf(s_a[c + k], v[k], acc[k]);
+    }
+    npart[((size_t)robot * groups + g) * planes + p] = sum_fixed(acc);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // warp 0: S and Q of the group, lanes stride over the CTAs, fixed shuffle tree
     float S = 0.f, Q = 0.f;
-    for (int c = c0; c < c1; ++c) {
-      const float a = s_a[c - c0];
+    for (int c = threadIdx.x; c < nc; c += 32) {
+      const float a = s_a[c];
       S = fmaf(a, part[(size_t)c * part_stride + 1], S);
       Q = fmaf(a * a, part[(size_t)c * part_stride + 2], Q);
     }
-    wpart[((size_t)robot * groups + g) * 2] = S;
-    wpart[((size_t)robot * groups + g) * 2 + 1] = Q;
+    S = warp_sum(S);
+    Q = warp_sum(Q);
+    if (threadIdx.x == 0) {
+      wpart[((size_t)robot * groups + g) * 2] = S;
+      wpart[((size_t)robot * groups + g) * 2 + 1] = Q;
+    }
   }
 }
 
-int cta_rescale_groups(int n_cta) { return (n_cta + kRescaleMaxCtas - 1) / kRescaleMaxCtas; }
+// ---- the whole tail in one launch (fused-controls path) ----------------------------------------------------------
+// grid = (groups, robots).  Every block rescales its group (above); the block that finishes last for a robot sums the
+// groups in fixed order into the robot's record {c_min, S, Q, -, N[P]} and, MODE 0 (unsharded), merges it: u = N / S ->
+// u_new, warm start, stats.  The block that finishes last of the whole grid advances the solve counter and, MODE 1
+// (peer exchange), first runs exchange_and_merge for all robots.  MODE 2: records only (NCCL all-gather + merge follow).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    rescale_tail_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
+                        unsigned int *__restrict__ cmin, float *__restrict__ wpart, float *__restrict__ npart,
+                        float *__restrict__ record, float *__restrict__ u_new, float *__restrict__ nominal,
+                        float *__restrict__ stats, uint32_t *__restrict__ counter, unsigned int *__restrict__ ticket,
+                        int planes, int n_cta, int part_stride, int groups, int per, int R, ExchangeArgs x) {
+  __shared__ float s_a[kRescaleMaxCtas];
+  __shared__ float s_S;
+  const int robot = blockIdx.y;
+  rescale_group(hdr, cta_part, cmin, wpart, npart, planes, n_cta, part_stride, groups, per, robot, blockIdx.x, s_a);
+  if (!last_block_of_grid(ticket + 1 + robot, gridDim.x)) return;
+  // last block of this robot: fixed-order sums over the groups (__ldcg: written by other blocks of this launch)
+  float *rec = record + (size_t)robot * part_stride;
+  if (threadIdx.x < 32) {
+    const float *wp = wpart + (size_t)robot * groups * 2;
+    float a = 0.f, b = 0.f;
+    for (int g = threadIdx.x; g < groups; g += 32) {
+      a += __ldcg(wp + 2 * g);
+      b += __ldcg(wp + 2 * g + 1);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) {
+      const float m = ordered_to_float(cmin[robot]);
+      cmin[robot] = 0xFFFFFFFFu;  // every block of this robot has read it: ready for the next solve's atomicMin
+      rec[0] = m;
+      rec[1] = a;
+      rec[2] = b;
+      rec[3] = 0.f;
+      if (MODE == 0) {
+        const float S = fmaf(1.f, a, 0.f), Q = fmaf(1.f, b, 0.f);  // merge_sums with one rank
+        s_S = S;
+        stats[robot * 4 + 0] = m;
+        stats[robot * 4 + 1] = S;
+        stats[robot * 4 + 2] = S * S / Q;
+        stats[robot * 4 + 3] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const int gm = (groups + kTailMlp - 1) / kTailMlp * kTailMlp;
+  for (int p = threadIdx.x; p < planes; p += blockDim.x) {
+    const float *np = npart + (size_t)robot * groups * planes + p;
+    float acc[kTailMlp];
+#pragma unroll
+    for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
+    for (int g = 0; g < gm; g += kTailMlp) {
+#pragma unroll
+      for (int k = 0; k < kTailMlp; ++k) acc[k] += (g + k < groups) ? __ldcg(np + (size_t)(g + k) * planes) : 0.f;
+    }
+    const float a = sum_fixed(acc);
+    rec[4 + p] = a;
+    if (MODE == 0) {
+      const float u = fmaf(1.f, a, 0.f) / s_S;  // merge_numerator with one rank
+      u_new[(size_t)robot * planes + p] = u;
+      if (nominal) nominal[(size_t)robot * planes + p] = u;  // un-shifted warm start, as the reference (DD:89-90)
+    }
+  }
+  if (R > 1 && !last_block_of_grid(ticket, (unsigned)R)) return;
+  // last block of the solve
+  if (MODE == 1) {
+    exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R);
+  } else if (MODE == 0) {
+    if (threadIdx.x == 0) *counter = *counter + 1u;
+  }
+}
 
-cudaError_t launch_cta_rescale(const DeviceState &d, cudaStream_t s) {
+// CTA records per block of the one-kernel tail: enough blocks to spread the read of the records, few enough groups for
+// the last block's final sums
+static int tail_groups(int n_cta, int R) {
+  int per = kRescaleMaxCtas;
+  if (R < 64) {
+    per = 32;
+    while (per < kRescaleMaxCtas && (n_cta + per - 1) / per > 64) per *= 2;
+  }
+  return (n_cta + per - 1) / per;
+}
+
+cudaError_t launch_rescale_tail(const DeviceState &d, int mode, cudaStream_t s) {
   const int n_cta = (d.K + 127) / 128;
-  dim3 grid(cta_rescale_groups(n_cta), d.R);
-  cta_rescale_kernel<<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.wpart, d.npart, d.planes, n_cta, d.rec_stride,
-                                          (int)grid.x);
+  const int groups = tail_groups(n_cta, d.R);
+  const int per = (n_cta + groups - 1) / groups;
+  dim3 grid(groups, d.R);
+  float *nominal = d.feedback ? d.nominal : nullptr;
+  ExchangeArgs x = exchange_args(d);
+#define MPPI_LAUNCH_TAIL(M)                                                                                          \
+  rescale_tail_kernel<M><<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.wpart, d.npart, d.record, d.u_new, nominal, \
+                                              d.stats, d.counter, d.tail_ticket, d.planes, n_cta, d.rec_stride,      \
+                                              groups, per, d.R, x)
+  if (mode == 0) {
+    MPPI_LAUNCH_TAIL(0);
+  } else if (mode == 1) {
+    MPPI_LAUNCH_TAIL(1);
+  } else {
+    MPPI_LAUNCH_TAIL(2);
+  }
+#undef MPPI_LAUNCH_TAIL
   return cudaGetLastError();
 }
 
-// Tensor map of the noise tensor for the TMA ring: 2-D {Kp samples, R * planes rows} of f32, box {32, kStageSteps*U}.
+// Tensor map of the noise tensor for the TMA ring: 2-D {Kp samples, B * R * planes rows} of f32, box {32, kStageSteps*U}.
 // cuTensorMapEncodeTiled is taken from the driver through the runtime (no link-time dependency on libcuda).
 cudaError_t make_eps_tensor_map(DeviceState &d) {
   d.eps_map_valid = false;
@@ -916,7 +941,7 @@ cudaError_t make_eps_tensor_map(DeviceState &d) {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess) return e;
   if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-  const cuuint64_t gdim[2] = {(cuuint64_t)d.Kp, (cuuint64_t)d.R * (cuuint64_t)d.planes};
+  const cuuint64_t gdim[2] = {(cuuint64_t)d.Kp, (cuuint64_t)d.eps_buffers * (cuuint64_t)d.R * (cuuint64_t)d.planes};
   const cuuint64_t gstride[1] = {(cuuint64_t)d.Kp * sizeof(float)};
   const cuuint32_t box[2] = {32u, (cuuint32_t)(kStageSteps * d.U)};
   const cuuint32_t estride[2] = {1u, 1u};
@@ -928,58 +953,60 @@ cudaError_t make_eps_tensor_map(DeviceState &d) {
   return cudaSuccess;
 }
 
-cudaError_t launch_rollout_cost_tma(const DeviceState &d, bool fused, cudaStream_t s) {
+cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, bool write_nearest, cudaStream_t s) {
+  if (!d.eps_map_valid) return cudaErrorNotSupported;
   dim3 grid((d.K + 127) / 128, d.R);
   const size_t smem = pruned_tma_smem_bytes(d.T, d.planes, d.U);
-#define MPPI_LAUNCH_TMA(M)                                                                                       \
+  int *nearest = write_nearest ? d.nearest : nullptr;
+#define MPPI_LAUNCH_TMA(M, TAP)                                                                                  \
   do {                                                                                                           \
     if (smem > 48 * 1024) {                                                                                      \
-      cudaError_t e = cudaFuncSetAttribute(rollout_cost_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem);                                                           \
+      cudaError_t e = cudaFuncSetAttribute(rollout_cost_tma_kernel<M, TAP>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
     }                                                                                                            \
-    rollout_cost_tma_kernel<M><<<grid, 128, smem, s>>>(d.eps_map, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, \
-                                                       d.grid_cells, d.cost, d.cmin, d.K, d.planes, d.win_stride, \
-                                                       d.T, d.grid_max_cells, d.eps, d.Kp,                       \
-                                                       fused ? d.cta_part : nullptr, d.rec_stride);              \
+    rollout_cost_tma_kernel<M, TAP><<<grid, 128, smem, s>>>(                                                     \
+        d.eps_map, d.bounds, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, d.grid_cells, d.cost, d.cmin, d.K, \
+        d.planes, d.win_stride, d.T, d.grid_max_cells, d.eps, d.Kp, fused ? d.cta_part : nullptr, d.rec_stride,  \
+        d.counter, (uint32_t)(d.eps_buffers - 1), d.eps_buf_elems, nearest);                                     \
   } while (0)
-  switch (d.model) {
-    case kDiffDrive: MPPI_LAUNCH_TMA(kDiffDrive); break;
-    case kSteering: MPPI_LAUNCH_TMA(kSteering); break;
-    default: MPPI_LAUNCH_TMA(kFullBody); break;
+#define MPPI_LAUNCH_TMA_MODEL(TAP)                                                                               \
+  switch (d.model) {                                                                                             \
+    case kDiffDrive: MPPI_LAUNCH_TMA(kDiffDrive, TAP); break;                                                    \
+    case kSteering: MPPI_LAUNCH_TMA(kSteering, TAP); break;                                                      \
+    default: MPPI_LAUNCH_TMA(kFullBody, TAP); break;                                                             \
   }
+  if (nearest) { MPPI_LAUNCH_TMA_MODEL(true) } else { MPPI_LAUNCH_TMA_MODEL(false) }
+#undef MPPI_LAUNCH_TMA_MODEL
 #undef MPPI_LAUNCH_TMA
   return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, cudaStream_t s) {
-  if (d.eps_map_valid && d.k2_ring == 1) return launch_rollout_cost_tma(d, fused, s);
-  dim3 grid((d.K + 127) / 128, d.R);
-  const size_t smem = pruned_smem_bytes(d.T, d.planes, d.U);
-#define MPPI_LAUNCH_PRUNED(M)                                                                                    \
-  do {                                                                                                           \
-    if (smem > 48 * 1024) {                                                                                      \
-      cudaError_t e = cudaFuncSetAttribute(rollout_cost_pruned_kernel<M>,                                        \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-      if (e != cudaSuccess) return e;                                                                            \
-    }                                                                                                            \
-    rollout_cost_pruned_kernel<M><<<grid, 128, smem, s>>>(d.hdr, d.eps, d.nominal, d.window, d.state,            \
-                                                          d.grid_hdr, d.grid_cells, d.cost, d.cmin, d.K, d.Kp,   \
-                                                          d.planes, d.win_stride, d.T, d.grid_max_cells);        \
-  } while (0)
-  switch (d.model) {
-    case kDiffDrive: MPPI_LAUNCH_PRUNED(kDiffDrive); break;
-    case kSteering: MPPI_LAUNCH_PRUNED(kSteering); break;
-    default: MPPI_LAUNCH_PRUNED(kFullBody); break;
-  }
-#undef MPPI_LAUNCH_PRUNED
-  return cudaGetLastError();
+int rollout_carveout_percent(const DeviceState &d) {
+  const size_t dyn = pruned_tma_smem_bytes(d.T, d.planes, d.U);
+  const void *fn = d.model == kDiffDrive ? (const void *)rollout_cost_tma_kernel<kDiffDrive, false>
+                   : d.model == kSteering ? (const void *)rollout_cost_tma_kernel<kSteering, false>
+                                          : (const void *)rollout_cost_tma_kernel<kFullBody, false>;
+  if (dyn > 48 * 1024 &&
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+    return -1;
+  cudaFuncAttributes attr;
+  int ctas = 0, dev = 0, max_smem = 0;
+  if (cudaFuncGetAttributes(&attr, fn) != cudaSuccess) return -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return -1;
+  // what the resident CTAs of K2 need -- assuming the split is not the limiter (the driver sizes it the same way)
+  const int by_regs = attr.numRegs > 0 ? 65536 / (attr.numRegs * 128) : 16;
+  const size_t per_cta = dyn + attr.sharedSizeBytes + 1024;  // + the per-CTA reservation
+  ctas = by_regs < 16 ? by_regs : 16;
+  while (ctas > 1 && per_cta * ctas > (size_t)max_smem) --ctas;
+  int pct = (int)((per_cta * ctas * 100 + max_smem - 1) / max_smem);
+  return pct > 100 ? 100 : pct;
 }
 
 // worth it only for windows of more than a couple of dozen points; the 16-bit pair fields bound T
 bool pruned_scan_supported(int T, int planes) {
-  return T >= 24 && T <= 4096 && pruned_smem_bytes(T, planes, kMaxControls) <= 200 * 1024 &&
-         pruned_tma_smem_bytes(T, planes, kMaxControls) <= 200 * 1024;
+  return T >= 24 && T <= 4096 && pruned_tma_smem_bytes(T, planes, kMaxControls) <= 200 * 1024;
 }
 
 }  // namespace mppi

@@ -69,9 +69,10 @@ typedef enum {
 } mppi_debug_flags;
 
 /* Implementation of the nearest-window-point scan inside the fused rollout+cost kernel. Both are exact and
- * bit-identical in every output; LITERAL evaluates all T window points per state (DD:186-190), PRUNED only the
- * points that a per-solve candidate grid cannot rule out.  AUTO = PRUNED when T >= 24, LITERAL below; LITERAL is
- * forced while MPPI_DEBUG_NEAREST is on (it is the kernel that records the argmin). */
+ * bit-identical in every output (cost and, with MPPI_DEBUG_NEAREST, the argmin index: first minimum wins,
+ * DD:186-190); LITERAL evaluates all T window points per state, PRUNED only the points that a per-solve candidate
+ * grid cannot rule out.  AUTO = PRUNED when T >= 24, LITERAL below; LITERAL is forced while MPPI_DEBUG_STATES is on
+ * (it is the kernel that records the predicted states). */
 typedef enum {
   MPPI_SCAN_AUTO = 0,
   MPPI_SCAN_LITERAL = 1,
@@ -86,6 +87,37 @@ typedef enum {
   MPPI_WINDOW_HOST = 1,
   MPPI_WINDOW_DEVICE = 2
 } mppi_window_builder;
+
+/* Tuning and behaviour switches of one handle (mppi_set_option / mppi_get_option); values are doubles, integer
+ * options take the integral value.  Every option has a working default: none is needed for a correct solve, and none
+ * is read from the process environment. */
+typedef enum {
+  MPPI_OPT_GRID_MAX_CELLS = 1,      /* cells of the candidate grid per robot (pruned scan), 256 .. 262144; default
+                                       clamp(num_samples / 2, 256, 65536).  Re-allocates the cell table. */
+  MPPI_OPT_GRID_H_MIN = 2,          /* smallest grid cell side [m], > 0; default 0.05 */
+  MPPI_OPT_GRID_MARGIN = 3,         /* margin around the window's bounding box [m]; 0 (default) = a quarter of the
+                                       horizon reach v_ref * dt * (T-1) */
+  MPPI_OPT_GRID_LANES = 4,          /* lanes per cell of the grid builder: 0 (default) = by the handle's cell count,
+                                       or 1, 2, 4, 8, 16, 32 */
+  MPPI_OPT_REDUCE_GROUPS = 5,       /* plane groups one block of the weighted-control reduction walks through;
+                                       0 (default) = by the number of blocks */
+  MPPI_OPT_FUSE_CONTROLS = 6,       /* weighted controls reduced per CTA inside the rollout kernel (1) or by the separate
+                                       weight + reduction kernels (0); -1 (default) = by problem shape */
+  MPPI_OPT_NOISE_PREFETCH = 7,      /* 1: the normals of solve n+1 are generated on a second stream while solve n runs
+                                       (double-buffered tensor; same Philox stream, same results); 0: generated at the
+                                       start of their own solve; -1 (default) = on when the pruned scan is used and
+                                       the second tensor fits in device memory */
+  MPPI_OPT_EXCHANGE_TIMEOUT_MS = 8, /* peer exchange (mppi_comm_connect): how long the merge waits for a peer's record
+                                       before the solve fails with MPPI_ERR_NCCL; default 2000 */
+  MPPI_OPT_FEEDBACK_WARM_START = 9, /* 1 (default): the new controls become the warm start of the next mppi_enqueue, as
+                                       the reference's optimal_solution does (DD:89-90); 0: every mppi_enqueue starts
+                                       from the warm start of the last mppi_upload (a host that shifts or resets the
+                                       sequence itself; repeated identical solves) */
+  MPPI_OPT_UPLOAD_WARM_START = 10   /* 1 (default): mppi_solve reads u_nominal on entry (in/out, like the reference's
+                                       optimal_solution member); 0: after the first solve the warm start is the
+                                       device's own copy of the previous result and u_nominal is output only -- saves
+                                       the conversion and the upload of n_robots x (T-1) x U values per cycle */
+} mppi_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
 
@@ -104,6 +136,9 @@ int mppi_set_params(mppi_handle h, const mppi_params *params);
 int mppi_set_debug(mppi_handle h, int debug_flags);
 int mppi_set_scan_mode(mppi_handle h, int scan_mode);
 int mppi_set_window_builder(mppi_handle h, int mode);
+/* MPPI_ERR_INVALID for an unknown option or a value outside the documented range (the handle is left unchanged). */
+int mppi_set_option(mppi_handle h, int option, double value);
+int mppi_get_option(mppi_handle h, int option, double *value);
 
 /* ---- inputs -------------------------------------------------------------------------------------------- */
 
@@ -148,7 +183,9 @@ int mppi_download(mppi_handle h, double *u_nominal);
 int mppi_synchronize(mppi_handle h);
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of the handle's own. NULL = default. */
 int mppi_set_stream(mppi_handle h, void *cuda_stream);
-/* Capture upload-less enqueue into a CUDA graph and replay it on later mppi_enqueue calls (latency path). */
+/* Capture the solve into a CUDA graph and replay it on later calls: mppi_enqueue replays the kernels, mppi_solve
+ * the H2D copy + kernels + D2H copy.  Works for unsharded handles and for the NVLink peer exchange
+ * (mppi_comm_connect); handles on the NCCL transport (mppi_comm_init) keep plain stream launches. */
 int mppi_use_graph(mppi_handle h, int enable);
 
 /* ---- outputs beyond the controls (debug / parity) ------------------------------------------------------- */
@@ -166,10 +203,12 @@ int mppi_get_info(mppi_handle h, int *model, int *num_samples, int *horizon, int
 /* Per-kernel device time of the solve (CUDA events between the launches on the handle's stream), averaged over
  * n_iters solves after one warm-up: ms[0..5] = noise, rollout+cost, weights, weighted controls, finalize, merge
  * (collective time, when sharded, is included in ms[5]); ms[6] = whole enqueue; ms[7] = candidate grid of the
- * pruned scan (0 when the literal scan runs).  Advances the warm start and the solve counter like n_iters + 1
- * calls of mppi_enqueue. */
+ * pruned scan (0 when the literal scan runs).  The kernels run one after the other here (no second stream), so the
+ * sum exceeds the time of a pipelined mppi_enqueue.  Side effects: runs n_iters + 1 REAL solves -- the warm start
+ * and the solve counter advance exactly as by n_iters + 1 calls of mppi_enqueue. */
 int mppi_time_kernels(mppi_handle h, int n_iters, float *ms /* [8] */);
-/* bytes one mppi_solve moves: host -> device (header, windows, states, warm start) and device -> host (controls, stats) */
+/* bytes the last mppi_solve / mppi_upload moved host -> device (header, poses, state records; the warm start when the
+ * host supplies it; the windows when they are built on the host) and one solve moves device -> host (controls, stats) */
 int mppi_get_io_bytes(mppi_handle h, size_t *h2d_bytes, size_t *d2h_bytes);
 /* number of kernel launches issued by the last mppi_enqueue (bench.py's gpu_launches claim) */
 int mppi_last_launch_count(mppi_handle h);
@@ -184,7 +223,9 @@ int mppi_comm_init(mppi_handle h, const void *id, int rank, int n_ranks);
  * MPPI_IPC_HANDLE_BYTES), the launcher all-gathers the handles, every rank connects.  Afterwards the finalize
  * kernel of a solve stores this rank's record straight into every peer's buffer and raises a flag there; the merge
  * kernel waits for the flags.  One process per GPU; every rank must call mppi_solve / mppi_enqueue the same number
- * of times (a missing peer makes the solve return MPPI_ERR_NCCL after a ~2 s device-side timeout). */
+ * of times, and the ranks should pass a barrier between mppi_comm_connect and their first solve.  A peer whose
+ * record does not arrive within MPPI_OPT_EXCHANGE_TIMEOUT_MS (default 2 s, device-side) fails the solve: the warm
+ * start keeps its previous value, and mppi_solve / mppi_download / mppi_synchronize return MPPI_ERR_NCCL. */
 #define MPPI_IPC_HANDLE_BYTES 64
 int mppi_comm_export(mppi_handle h, int n_ranks, void *handle_out /* MPPI_IPC_HANDLE_BYTES */);
 int mppi_comm_connect(mppi_handle h, const void *handles /* n_ranks x MPPI_IPC_HANDLE_BYTES */, int rank, int n_ranks);

@@ -84,15 +84,16 @@ int twin_rollout_cost(int model, const mppi_params *p, int K, int T, const doubl
   if (model < 0 || model > 2 || !p || K < 1 || T < 2 || !state || !window || !eps || !u_nominal || !cost) return -1;
   SolveParams P = make_solve_params(model, T, *p, dt);
   std::vector<float> win(2 * (size_t)T), nom((size_t)(T - 1) * P.U);
-  float st[8];
+  float rec[4];  // the device's state record {yaw, roll, pitch, -}; the rollout starts at the origin of the robot frame
   window_to_robot_frame(window, T, state[0], state[1], win.data());
-  state_to_robot_frame(model, state, st);
-  st[5] = yaw_ref0_f32(win[0], win[1], win[2], win[3]);  // what the kernels derive from the same FP32 window
+  state_to_robot_frame(model, state, rec);
+  const float st[5] = {0.f, 0.f, rec[0], rec[1], rec[2]};
+  const float yaw_ref0 = yaw_ref0_f32(win[0], win[1], win[2], win[3]);  // what the kernels derive from the same FP32 window
   for (size_t k = 0; k < nom.size(); ++k) nom[k] = (float)u_nominal[k];
   switch (model) {
-    case kDiffDrive: run<kDiffDrive>(P, K, st, st[5], win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
-    case kSteering: run<kSteering>(P, K, st, st[5], win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
-    default: run<kFullBody>(P, K, st, st[5], win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
+    case kDiffDrive: run<kDiffDrive>(P, K, st, yaw_ref0, win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
+    case kSteering: run<kSteering>(P, K, st, yaw_ref0, win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
+    default: run<kFullBody>(P, K, st, yaw_ref0, win.data(), eps, nom.data(), cost, nearest, d2, states, zmp, controls); break;
   }
   return 0;
 }

@@ -32,12 +32,14 @@ def _worker(rank, world, port, out_dir):
     K, T = 4096, 40
     case = make_case("steering", K, T, seed=31)
     res = {}
-    for mode in ("p2p", "nccl"):
+    for mode in ("p2p", "p2p_graph", "p2p_fused", "nccl", "nccl_fused"):
         ctl = CONTROLLERS["steering"](launch=True, device=rank, horizon=T, num_samples=K // world)
         ctl.set_path(case["path"])
         ctl.set_seed(77, 0)
         ctl.set_shard(rank * (K // world), K, 0)
-        if mode == "p2p":
+        ctl.use_graph(mode == "p2p_graph")  # the peer exchange replays from a CUDA graph; NCCL keeps stream launches
+        ctl.set_option(_capi.OPT_FUSE_CONTROLS, 1 if mode.endswith("fused") else 0)
+        if mode.startswith("p2p"):
             t = torch.frombuffer(bytearray(ctl.comm_export(world)), dtype=torch.uint8).cuda()
             allh = [torch.zeros_like(t) for _ in range(world)]
             dist.all_gather(allh, t)
@@ -48,11 +50,16 @@ def _worker(rank, world, port, out_dir):
                 idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
             dist.broadcast(idt, 0)
             ctl.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        dist.barrier()
         us = [ctl.solve(case["state"], case["dt"]).copy() for _ in range(4)]
         res[mode] = np.stack(us)
         dist.barrier()
         ctl.close()
     assert np.array_equal(res["p2p"], res["nccl"])
+    assert np.array_equal(res["p2p"], res["p2p_graph"])
+    assert np.array_equal(res["p2p_fused"], res["nccl_fused"])
+    rng_ = np.array(case["sp"]["u_max"][:3]) - np.array(case["sp"]["u_min"][:3])
+    assert (np.abs(res["p2p"] - res["p2p_fused"]) / rng_).max() < 5e-4  # per-CTA vs per-chunk summation order
     np.save(os.path.join(out_dir, f"u_{rank}.npy"), res["p2p"])
     dist.barrier()
     dist.destroy_process_group()

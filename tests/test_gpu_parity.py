@@ -345,25 +345,30 @@ def test_pruned_scan_bit_identical_to_literal_and_twin(model, K, T):
 
 @pytest.mark.parametrize("model,K,T", [("diff_drive", 1000, 26), ("diff_drive", 4099, 101), ("steering", 333, 50),
                                        ("full_body", 1030, 27), ("full_body", 520, 100), ("steering", 2048, 24)])
-def test_noise_ring_variants_bit_identical(model, K, T, monkeypatch):
-    """K2 streams the normals either through per-warp TMA tiles (default) or a per-thread cp.async ring: same
-    per-sample cost bits, equal to the FP32 twin -- with partial warps (K not a multiple of 32), odd horizons and
-    horizons whose step count is not a multiple of the 4-step TMA stage."""
+def test_tma_ring_ragged_shapes_bit_identical_to_twin_and_literal(model, K, T):
+    """K2 streams the normals through per-warp TMA tiles of {32 samples} x {4 control steps}: partial warps (K not a
+    multiple of 32), odd horizons and horizons whose step count is not a multiple of the 4-step stage must give the
+    literal kernel's (plain global loads) and the FP32 twin's per-sample cost bits, and the same argmin indices."""
     case = make_case(model, K, T, seed=5)
     got = {}
-    for ring in ("1", "0"):
-        monkeypatch.setenv("MPPI_K2_RING", ring)
+    for mode in (_capi.SCAN_PRUNED, _capi.SCAN_LITERAL):
         with _make_ctl(case) as ctl:
             ctl.set_noise(case["eps"][None])
+            ctl.set_scan_mode(mode)
+            ctl.set_debug(_capi.DEBUG_NEAREST)
             ctl.optimal_solution[0] = case["u0"]
             u = ctl.solve(case["state"], case["dt"]).copy()
             window, _ = ctl.window()
-            got[ring] = (ctl.costs(), u)
-    assert np.array_equal(got["0"][0].view(np.uint32), got["1"][0].view(np.uint32))
-    # controls: the TMA path reduces them per CTA inside K2, the cp.async path in K3 + K4 (summation order differs)
-    assert np.abs(got["0"][1] - got["1"][1]).max() <= 2e-5 * _urange(case).max()
-    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"])
-    assert np.array_equal(got["1"][0].view(np.uint32), tw["cost"].view(np.uint32))
+            got[mode] = (ctl.costs(), u, ctl.nearest())
+    lit, pru = got[_capi.SCAN_LITERAL], got[_capi.SCAN_PRUNED]
+    assert np.array_equal(lit[0].view(np.uint32), pru[0].view(np.uint32))
+    assert np.array_equal(lit[2], pru[2])
+    assert np.abs(lit[1] - pru[1]).max() <= 2e-5 * _urange(case).max()
+    tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"],
+                                  want=("nearest",))
+    assert np.array_equal(pru[0].view(np.uint32), tw["cost"].view(np.uint32))
+    Tc = T - 2 if model == "full_body" else T
+    assert np.array_equal(pru[2][:, :Tc], tw["nearest"][:, :Tc])
 
 
 @pytest.mark.parametrize("model,overrides,dt", [
@@ -392,15 +397,17 @@ def test_large_angles_take_the_general_instantiation(model, overrides, dt):
 
 @pytest.mark.parametrize("model,K,T,R", [("diff_drive", 1024, 50, 3), ("diff_drive", 4099, 101, 1), ("steering", 333, 50, 2),
                                          ("full_body", 1030, 27, 1), ("full_body", 2048, 100, 1)])
-def test_fused_weighted_controls_match_the_separate_kernels(model, K, T, R, monkeypatch):
-    """Many-robot handles reduce the weighted controls inside K2 (per-CTA records against the CTA's own minimum, then
-    a log-sum-exp rescale) instead of K3 + K4.  Forced on and off here: same costs, same c_min, controls / sum w / ESS
-    equal up to FP32 summation order, three chained solves."""
+def test_fused_weighted_controls_match_the_separate_kernels(model, K, T, R):
+    """Many-robot handles and mid-sized single solves reduce the weighted controls inside K2 (per-CTA records against
+    the CTA's own minimum, then a log-sum-exp rescale + finalize + merge in one tail kernel) instead of K3 + K4 + K5 +
+    K6.  Forced on and off here (MPPI_OPT_FUSE_CONTROLS): same costs, same c_min, controls / sum w / ESS equal up to
+    FP32 summation order, three chained solves."""
     case = make_case(model, K, T, seed=17)
     runs = {}
     for fused in ("0", "1"):
-        monkeypatch.setenv("MPPI_FUSE_CONTROLS", fused)
         with _make_ctl(case, n_robots=R) as ctl:
+            ctl.set_option(_capi.OPT_FUSE_CONTROLS, int(fused))
+            assert ctl.get_option(_capi.OPT_FUSE_CONTROLS) == int(fused)
             ctl.set_seed(99, 0)
             states = np.tile(case["state"], (R, 1))
             states[:, 0] += 0.05 * np.arange(R)
@@ -776,3 +783,214 @@ def test_full_size_full_body_config_against_the_oracle():
     o = oracle.solve("full_body", case["sp"], K, T, case["state"], case["dt"], case["path"], eps, case["u0"], nthreads=8)
     assert np.all(np.abs(cost - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
     assert (np.abs(u_gpu - o["u_new"]) / _urange(case)).max() <= U_TOL
+
+
+# ---- round 2: argmin tap of the production kernel, noise prefetch, options -------------------------------------
+
+@pytest.mark.parametrize("model,K,T", [("diff_drive", 2048, 100), ("steering", 1024, 50), ("full_body", 1024, 64)])
+def test_pruned_scan_records_the_literal_argmin(model, K, T):
+    """MPPI_DEBUG_NEAREST on the production (pruned, TMA) kernel: the index it records is the literal scan's first
+    minimum (diff_drive_mppi.cpp:186-190) for every window shape that stresses the pruning bounds, and differs from
+    the FP64 oracle's index only at near-ties of the two smallest distances."""
+    rng = np.random.default_rng(K + T)
+    case = make_case(model, K, T, seed=23)
+    Tc = T - 2 if model == "full_body" else T
+    for name, xy in _windows_for_pruning(T, rng).items():
+        window = np.concatenate([xy, np.zeros((T, 1))], 1)
+        near = {}
+        for mode in (_capi.SCAN_LITERAL, _capi.SCAN_PRUNED):
+            with _make_ctl(case) as ctl:
+                ctl.set_window(window)
+                ctl.set_noise(case["eps"][None])
+                ctl.set_scan_mode(mode)
+                ctl.set_debug(_capi.DEBUG_NEAREST)
+                ctl.optimal_solution[0] = case["u0"]
+                ctl.solve(case["state"], case["dt"])
+                near[mode] = ctl.nearest()[:, :Tc]
+        assert np.array_equal(near[_capi.SCAN_LITERAL], near[_capi.SCAN_PRUNED]), name
+        tw = oracle.twin_rollout_cost(model, case["sp"], K, T, case["state"], case["dt"], window, case["eps"], case["u0"],
+                                      want=("nearest",))
+        assert np.array_equal(near[_capi.SCAN_PRUNED], tw["nearest"][:, :Tc]), name
+    # against FP64 on the path-built window (the oracle builds its own): mismatches are near-ties only
+    with _make_ctl(case) as ctl:
+        ctl.set_noise(case["eps"][None])
+        ctl.set_scan_mode(_capi.SCAN_PRUNED)
+        ctl.set_debug(_capi.DEBUG_NEAREST | _capi.DEBUG_NONE)
+        ctl.optimal_solution[0] = case["u0"]
+        ctl.solve(case["state"], case["dt"])
+        near_gpu = ctl.nearest()[:, :Tc]
+    o = oracle.solve(model, case["sp"], K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"],
+                     want=("nearest", "states", "window"))
+    mism = near_gpu != o["nearest"][:, :Tc]
+    assert mism.mean() < 1e-3
+    if mism.any():  # every mismatch is a tie of the two candidate points within FP32 resolution
+        win = o["window"][:, :2]
+        st = o["states"][:, :Tc, :2]
+        ii, tt = np.nonzero(mism)
+        pa, pb = win[near_gpu[ii, tt]], win[o["nearest"][ii, tt]]
+        da = ((st[ii, tt] - pa) ** 2).sum(1)
+        db = ((st[ii, tt] - pb) ** 2).sum(1)
+        assert np.all(np.abs(da - db) <= 1e-5 * np.maximum(da, db) + 1e-12)
+
+
+def test_nearest_tap_at_full_size_stripes():
+    """K = 2^20, T = 100 (BASELINE config 4): the argmin tap of the production kernel against the FP32 twin on
+    stripes of the sample range (the first, a middle and the last 256 samples), internal Philox noise."""
+    import torch
+    K, T = 1 << 20, 100
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 6 * (1 << 30):
+        pytest.skip("needs ~3 GB of device memory")
+    case = make_case("diff_drive", 64, T, seed=3)
+    ctl = CONTROLLERS["diff_drive"](launch=True, horizon=T, num_samples=K)
+    ctl.set_path(case["path"])
+    ctl.set_seed(0x5EED0000 + 4, 0)
+    ctl.set_debug(_capi.DEBUG_NEAREST)
+    ctl.optimal_solution[0] = case["u0"]
+    ctl.solve(case["state"], case["dt"])
+    near, eps, cost = ctl.nearest(), ctl.noise(), ctl.costs()
+    window, _ = ctl.window()
+    ctl.close()
+    for lo in (0, K // 2 - 128, K - 256):
+        sl = slice(lo, lo + 256)
+        tw = oracle.twin_rollout_cost("diff_drive", case["sp"], 256, T, case["state"], case["dt"], window,
+                                      np.ascontiguousarray(eps[:, sl]), case["u0"], want=("nearest",))
+        assert np.array_equal(near[sl], tw["nearest"])
+        assert np.array_equal(cost[sl].view(np.uint32), tw["cost"].view(np.uint32))
+
+
+@pytest.mark.parametrize("model,K,T,R", [("diff_drive", 4096, 60, 1), ("steering", 40000, 30, 1), ("diff_drive", 600, 50, 9)])
+def test_noise_prefetch_is_bit_identical(model, K, T, R):
+    """MPPI_OPT_NOISE_PREFETCH: the normals of solve n+1 generated on the second stream while solve n runs (double
+    buffered tensor) are the same Philox stream -- noise, costs and controls of five chained solves are bit-identical
+    to the run that generates them at the start of their own solve; graph replay and the split API included."""
+    case = make_case(model, K, T, seed=29)
+    states = np.tile(case["state"], (R, 1))
+    states[:, 0] += 0.03 * np.arange(R)
+    runs = {}
+    for mode in ("off", "on", "on_graph", "on_split"):
+        with _make_ctl(case, n_robots=R) as ctl:
+            ctl.set_option(_capi.OPT_NOISE_PREFETCH, 0 if mode == "off" else 1)
+            ctl.set_seed(4242, 3)
+            ctl.use_graph(mode == "on_graph")
+            us, es, cs = [], [], []
+            for it in range(5):
+                if mode == "on_split":
+                    ctl.upload(states, case["dt"], with_nominal=(it == 0))
+                    ctl.enqueue()
+                    us.append(ctl.download().copy())
+                else:
+                    us.append(ctl.solve(states, case["dt"]).copy())
+                if it in (0, 3, 4):
+                    es.append(ctl.noise(R - 1))
+                    cs.append(ctl.costs(R - 1))
+                if it == 2:  # re-seeding in the middle invalidates the prefetched tensor
+                    ctl.set_seed(777, 11)
+            runs[mode] = (np.stack(us), np.stack(es), np.stack(cs))
+    ref = runs["off"]
+    assert not np.array_equal(ref[1][0], ref[1][1])
+    for mode in ("on", "on_graph", "on_split"):
+        assert np.array_equal(runs[mode][1], ref[1]), mode
+        assert np.array_equal(runs[mode][2].view(np.uint32), ref[2].view(np.uint32)), mode
+        assert np.array_equal(runs[mode][0], ref[0]), mode
+
+
+def test_weights_tap_after_graph_replays_on_the_fused_path():
+    """mppi_get_weights on the fused-controls path recomputes the weights on demand; a CUDA-graph replay must
+    invalidate an earlier on-demand result (it used to return the previous solve's weights)."""
+    case = make_case("diff_drive", 1024, 50, seed=31)
+    R = 8
+    states = np.tile(case["state"], (R, 1))
+    with _make_ctl(case, n_robots=R) as ctl:
+        ctl.set_seed(17, 0)
+        ctl.use_graph(True)
+        for _ in range(3):
+            ctl.solve(states, case["dt"])
+            w, c = ctl.weights(2), ctl.costs(2)
+            w64 = np.exp(-(c.astype(np.float64) - c.min()) / case["sp"]["lambda_"])
+            assert np.allclose(w, w64, rtol=2e-6, atol=1e-30)
+
+
+def test_feedback_warm_start_option():
+    """MPPI_OPT_FEEDBACK_WARM_START = 0: every enqueue starts from the uploaded warm start (the reference feeds
+    optimal_solution back, DD:89-90 -- the default)."""
+    case = make_case("diff_drive", 2048, 30, seed=37)
+    with _make_ctl(case) as ctl:
+        ctl.set_noise(case["eps"][None])
+        ctl.optimal_solution[0] = case["u0"]
+        ctl.upload(case["state"], case["dt"], with_nominal=True)
+        ctl.enqueue()
+        a = ctl.download().copy()
+        ctl.enqueue()
+        b = ctl.download().copy()
+        assert not np.array_equal(a, b)  # fed back: the second solve starts from the first one's controls
+        ctl.set_option(_capi.OPT_FEEDBACK_WARM_START, 0)
+        ctl.optimal_solution[0] = case["u0"]
+        ctl.upload(case["state"], case["dt"], with_nominal=True)
+        outs = []
+        for _ in range(3):
+            ctl.enqueue()
+            outs.append(ctl.download().copy())
+        assert np.array_equal(outs[0], a) and np.array_equal(outs[1], a) and np.array_equal(outs[2], a)
+
+
+def test_options_are_validated_and_nan_warm_start_is_rejected():
+    case = make_case("diff_drive", 512, 30)
+    with _make_ctl(case) as ctl:
+        for opt, bad in ((_capi.OPT_GRID_MAX_CELLS, 3), (_capi.OPT_GRID_MAX_CELLS, 1e9), (_capi.OPT_GRID_H_MIN, 0.0),
+                         (_capi.OPT_GRID_MARGIN, -1.0), (_capi.OPT_GRID_LANES, 3), (_capi.OPT_FUSE_CONTROLS, 2),
+                         (_capi.OPT_NOISE_PREFETCH, 5), (_capi.OPT_EXCHANGE_TIMEOUT_MS, 0.0),
+                         (_capi.OPT_FEEDBACK_WARM_START, 0.5), (99, 1), (_capi.OPT_GRID_H_MIN, float("nan"))):
+            with pytest.raises(_capi.MppiError) as e:
+                ctl.set_option(opt, bad)
+            assert e.value.code == _capi.MPPI_ERR_INVALID
+        ctl.set_noise(case["eps"][None])
+        u_ref = ctl.solve(case["state"], case["dt"]).copy()
+        cost_ref = ctl.costs()
+        # every grid geometry gives the same (exact) costs
+        for cells, lanes, hmin in ((256, 1, 0.05), (4096, 16, 0.2), (70000, 32, 0.02), (1024, 2, 0.05)):
+            ctl.set_option(_capi.OPT_GRID_MAX_CELLS, cells)
+            ctl.set_option(_capi.OPT_GRID_LANES, lanes)
+            ctl.set_option(_capi.OPT_GRID_H_MIN, hmin)
+            ctl.optimal_solution[...] = 0.0
+            u = ctl.solve(case["state"], case["dt"]).copy()
+            assert np.array_equal(ctl.costs().view(np.uint32), cost_ref.view(np.uint32)), (cells, lanes)
+            assert np.array_equal(u, u_ref)
+        ctl.optimal_solution[0, 3, 1] = np.nan
+        with pytest.raises(_capi.MppiError) as e:
+            ctl.solve(case["state"], case["dt"])
+        assert e.value.code == _capi.MPPI_ERR_INVALID and "warm start" in str(e.value)
+        ctl.optimal_solution[...] = 0.0
+        assert np.isfinite(ctl.solve(case["state"], case["dt"])).all()
+        km = ctl.time_kernels(2)
+        assert km["total"] > 0 and km["rollout_cost"] > 0
+
+
+@pytest.mark.parametrize("R,graph", [(1, False), (1, True), (9, True), (9, False)])
+def test_device_resident_warm_start_equals_the_uploaded_one(R, graph):
+    """MPPI_OPT_UPLOAD_WARM_START = 0: mppi_solve keeps the warm start on the device (the previous solve's result)
+    instead of converting and uploading the caller's copy every cycle: same controls, fewer bytes.  Many-robot handles
+    (device-built windows) then copy only header + poses + state records."""
+    K, T = 1024, 50
+    case = make_case("diff_drive", K, T, seed=41)
+    states = np.tile(case["state"], (R, 1))
+    states[:, 1] += 0.02 * np.arange(R)
+    runs, io = {}, {}
+    for upload in (1, 0):
+        with _make_ctl(case, n_robots=R) as ctl:
+            ctl.set_seed(2024, 0)
+            ctl.use_graph(graph)
+            ctl.set_option(_capi.OPT_UPLOAD_WARM_START, upload)
+            ctl.optimal_solution[...] = case["u0"]  # a non-zero first warm start must still reach the device
+            us = []
+            for it in range(4):
+                st = states.copy()
+                st[:, 0] += 0.05 * it
+                us.append(ctl.solve(st, case["dt"]).copy())
+            runs[upload] = np.stack(us)
+            io[upload] = ctl.io_bytes()
+    assert np.array_equal(runs[0], runs[1])
+    planes = (T - 1) * 2
+    assert io[1][0] - io[0][0] == 4 * R * planes  # the warm start is what no longer travels
+    if R >= 8:  # device-built windows: header + FP64 pose + state record per robot
+        assert io[0][0] == 256 + R * (16 + 16)
