@@ -16,6 +16,7 @@ SCAN_AUTO, SCAN_LITERAL, SCAN_PRUNED = 0, 1, 2
 WINDOW_AUTO, WINDOW_HOST, WINDOW_DEVICE = 0, 1, 2
 (OPT_GRID_MAX_CELLS, OPT_GRID_H_MIN, OPT_GRID_MARGIN, OPT_GRID_LANES, OPT_REDUCE_GROUPS, OPT_FUSE_CONTROLS,
  OPT_NOISE_PREFETCH, OPT_EXCHANGE_TIMEOUT_MS, OPT_FEEDBACK_WARM_START, OPT_UPLOAD_WARM_START) = range(1, 11)
+INFO_FUSED_CONTROLS = 100
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 

@@ -228,17 +228,18 @@ int effective_scan(mppi_handle h, bool *want_nearest, bool *want_states = nullpt
   return scan;
 }
 
-// K2 also produces the weighted-control records of its CTAs (then K3 + K4 are replaced by a rescale of the records).
-// AUTO: many-robot handles (K4 is far from the HBM roofline on many small tensors), and single solves whose K2 grid is
-// at most about two waves of CTAs but still covers the machine: there the CTAs' end phase runs in the shadow of the
-// slower CTAs of the same wave, while K3 + K4 would be two more dependent launches.  Large K keeps K4 (it runs at the
-// HBM roofline; the end phase would cost K2 what K4 saves), tiny K too (the pass would be serialised in a few CTAs).
+// K2 also produces the weighted-control records of its CTAs (then K3 + K4 + K5 + K6 become the one-kernel tail).
+// AUTO: many-robot handles (K4 is far from the HBM roofline on many small tensors), and single solves whose K2 grid
+// covers the machine (>= 256 CTAs, K >= 32768): the CTAs re-read their tile of the normals from L2 right after
+// streaming it, in the shadow of the CTAs that are still rolling out and of the next solve's generator, instead of a
+// second pass of the whole tensor through HBM plus two more dependent launches.  Measured with the noise prefetch on
+// (round 2, back-to-back solves): 0.517 vs 0.562 ms at K = 2^20, 0.096 vs 0.103 ms at 2^17, 0.062 vs 0.070 at 2^16.
+// Tiny K keeps K3 + K4: the pass would be serialised inside a few CTAs (K = 4096: 60 vs 51 us per synchronous solve).
 bool fused_controls(mppi_handle h, int scan) {
   if (scan != MPPI_SCAN_PRUNED || !h->d.cta_part) return false;
   if (h->opt_fuse_controls >= 0) return h->opt_fuse_controls != 0;
   if (h->R >= 8) return true;
-  const long long ctas = (long long)h->R * ((h->K + 127) / 128);
-  return ctas >= 256 && ctas <= 2048;
+  return (long long)h->R * ((h->K + 127) / 128) >= 256;
 }
 // noise prefetch: needs the second buffer (allocated at mppi_create when it fits) and the internal generator; the
 // pruned scan only (its K0 resets the minimum-cost slot; the literal path is the debug / tiny-horizon path)
@@ -814,6 +815,7 @@ int mppi_get_option(mppi_handle h, int option, double *value) {
     case MPPI_OPT_EXCHANGE_TIMEOUT_MS: *value = h->opt_timeout_ms; break;
     case MPPI_OPT_FEEDBACK_WARM_START: *value = d.feedback ? 1.0 : 0.0; break;
     case MPPI_OPT_UPLOAD_WARM_START: *value = h->opt_upload_warm_start; break;
+    case MPPI_INFO_FUSED_CONTROLS: *value = h->last_fused ? 1.0 : 0.0; break;
     default: return fail(h, MPPI_ERR_INVALID, "unknown option");
   }
   return MPPI_OK;

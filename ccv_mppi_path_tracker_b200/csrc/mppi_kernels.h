@@ -120,7 +120,7 @@ constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
 constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
 constexpr int kRescaleMaxCtas = 128;  // most CTA records folded by one block of rescale_tail_kernel
 static_assert(sizeof(SolveHeader) <= kHeaderBytes, "SolveHeader must fit its slot");
-static_assert(kRescaleMaxCtas % 16 == 0, "the tail reads the records sixteen at a time");
+static_assert(kRescaleMaxCtas % 32 == 0, "the tail reads the records thirty-two at a time");
 
 // K1  Philox4x32-10 + Box-Muller -> eps (float4 stores) of solve (counter + ahead), into that solve's buffer.
 cudaError_t launch_noise(const DeviceState &d, int ahead, cudaStream_t s);

@@ -768,9 +768,9 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
 // Brings the records of K2's CTAs to the robot's global minimum and folds them into partial sums:
 //   a_c = exp(-(m_c - c_min)/lambda);  wpart[g] = {sum_c a_c S_c, sum_c a_c^2 Q_c},  npart[g][p] = sum_c a_c N_c[p]
 // over the CTAs c of group g.  One block per (group, robot); thread = plane (coalesced over the records' rows),
-// sixteen independent accumulators per thread keep sixteen loads in flight (the tail is a chain of L2 round trips, not
-// bandwidth) and are combined in a fixed order (deterministic).
-constexpr int kTailMlp = 16;
+// kTailMlp independent accumulators per thread keep as many loads in flight (the tail is a chain of L2 round trips,
+// not bandwidth) and are combined in a fixed order (deterministic).
+constexpr int kTailMlp = 32;
 __device__ __forceinline__ float sum_fixed(const float (&a)[kTailMlp]) {
   float s[kTailMlp / 2];
 #pragma unroll
@@ -838,6 +838,62 @@ __global__ void __launch_bounds__(256)
   __shared__ float s_a[kRescaleMaxCtas];
   __shared__ float s_S;
   const int robot = blockIdx.y;
+  if (groups == 1 && MODE == 0) {
+    // Many-robot handles: one block owns the robot -- rescale, record and merge without leaving the block (no
+    // tickets, no fences, no partial arrays).  Same arithmetic and summation order as the general path below.
+    const float c_min = ordered_to_float(cmin[robot]);
+    const float inv_lambda = hdr->inv_lambda;
+    const float *part = cta_part + (size_t)robot * n_cta * part_stride;
+    for (int c = threadIdx.x; c < kRescaleMaxCtas; c += blockDim.x)
+      s_a[c] = c < n_cta ? expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda) : 0.f;
+    __syncthreads();
+    float *rec = record + (size_t)robot * part_stride;
+    if (threadIdx.x < 32) {
+      float S = 0.f, Q = 0.f;
+      for (int c = threadIdx.x; c < n_cta; c += 32) {
+        const float a = s_a[c];
+        S = fmaf(a, part[(size_t)c * part_stride + 1], S);
+        Q = fmaf(a * a, part[(size_t)c * part_stride + 2], Q);
+      }
+      S = warp_sum(S);
+      Q = warp_sum(Q);
+      if (threadIdx.x == 0) {
+        cmin[robot] = 0xFFFFFFFFu;  // re-armed for the next solve (every reader of this block is past the barrier)
+        rec[0] = c_min;
+        rec[1] = S;
+        rec[2] = Q;
+        rec[3] = 0.f;
+        const float Sm = fmaf(1.f, S, 0.f), Qm = fmaf(1.f, Q, 0.f);  // merge_sums with one rank
+        s_S = Sm;
+        stats[robot * 4 + 0] = c_min;
+        stats[robot * 4 + 1] = Sm;
+        stats[robot * 4 + 2] = Sm * Sm / Qm;
+        stats[robot * 4 + 3] = 0.f;
+        if (robot == 0) *counter = *counter + 1u;  // nothing reads it before the next solve's kernels
+      }
+    }
+    __syncthreads();
+    const float Sm = s_S;
+    const int ncm = (n_cta + kTailMlp - 1) / kTailMlp * kTailMlp;
+    for (int p = threadIdx.x; p < planes; p += blockDim.x) {
+      float acc[kTailMlp];
+#pragma unroll
+      for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
+      for (int c = 0; c < ncm; c += kTailMlp) {
+        float v[kTailMlp];
+#pragma unroll
+        for (int k = 0; k < kTailMlp; ++k) v[k] = part[(size_t)min(c + k, n_cta - 1) * part_stride + 4 + p];
+#pragma unroll
+        for (int k = 0; k < kTailMlp; ++k) acc[k] = fmaf(s_a[c + k], v[k], acc[k]);
+      }
+      const float a = sum_fixed(acc);
+      rec[4 + p] = a;
+      const float u = fmaf(1.f, a, 0.f) / Sm;  // merge_numerator with one rank
+      u_new[(size_t)robot * planes + p] = u;
+      if (nominal) nominal[(size_t)robot * planes + p] = u;
+    }
+    return;
+  }
   rescale_group(hdr, cta_part, cmin, wpart, npart, planes, n_cta, part_stride, groups, per, robot, blockIdx.x, s_a);
   if (!last_block_of_grid(ticket + 1 + robot, gridDim.x)) return;
   // last block of this robot: fixed-order sums over the groups (__ldcg: written by other blocks of this launch)

@@ -113,10 +113,13 @@ typedef enum {
                                        the reference's optimal_solution does (DD:89-90); 0: every mppi_enqueue starts
                                        from the warm start of the last mppi_upload (a host that shifts or resets the
                                        sequence itself; repeated identical solves) */
-  MPPI_OPT_UPLOAD_WARM_START = 10   /* 1 (default): mppi_solve reads u_nominal on entry (in/out, like the reference's
+  MPPI_OPT_UPLOAD_WARM_START = 10,  /* 1 (default): mppi_solve reads u_nominal on entry (in/out, like the reference's
                                        optimal_solution member); 0: after the first solve the warm start is the
                                        device's own copy of the previous result and u_nominal is output only -- saves
                                        the conversion and the upload of n_robots x (T-1) x U values per cycle */
+  MPPI_INFO_FUSED_CONTROLS = 100    /* read-only (mppi_get_option): 1 when the kernel sequence issued last reduced the
+                                       weighted controls inside the rollout kernel (what MPPI_OPT_FUSE_CONTROLS = -1
+                                       decided) */
 } mppi_option;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

@@ -991,6 +991,6 @@ def test_device_resident_warm_start_equals_the_uploaded_one(R, graph):
             io[upload] = ctl.io_bytes()
     assert np.array_equal(runs[0], runs[1])
     planes = (T - 1) * 2
-    assert io[1][0] - io[0][0] == 4 * R * planes  # the warm start is what no longer travels
+    assert 0 <= io[1][0] - io[0][0] - 4 * R * planes < 16  # the warm start (+ alignment) is what no longer travels
     if R >= 8:  # device-built windows: header + FP64 pose + state record per robot
         assert io[0][0] == 256 + R * (16 + 16)
