@@ -23,7 +23,9 @@ harness: $(PKG)/mppi_harness
 $(PKG)/mppi_harness: $(CSRC)/host/mppi_harness.cpp $(CSRC)/host/controllers.hpp $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ $(CSRC)/host/mppi_harness.cpp -L$(PKG) -lmppi_b200 -Wl,-rpath,'$$ORIGIN'
 
-hosttest: tests/host/fb_monitor_check
+hosttest: tests/host/fb_monitor_check tests/host/cmd_check
+tests/host/cmd_check: tests/host/cmd_check.cpp $(CSRC)/host/controllers.hpp include/mppi_b200.h $(LIB)
+	$(CXX) -O1 -std=c++17 -ffp-contract=off -Wall -o $@ tests/host/cmd_check.cpp -L$(PKG) -lmppi_b200 -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 tests/host/fb_monitor_check: tests/host/fb_monitor_check.cpp $(CSRC)/host/controllers.hpp include/mppi_b200.h
 	$(CXX) -O1 -std=c++17 -ffp-contract=off -Wall -o $@ tests/host/fb_monitor_check.cpp -L$(PKG) -lmppi_b200 -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 

@@ -253,6 +253,23 @@ class _MPPIBase:
     def cmd_vel(self, robot=0):
         return float(self.optimal_solution[robot, 0, 0]), float(self.optimal_solution[robot, 0, 1])
 
+    TREAD = 0.501  # tread_ (diff_drive_mppi.h:97)
+
+    def _steer_in_out(self, v, w, delta):
+        """Steering angles of the inner / outer wheel (steering_diff_drive_mppi.cpp:273-296, full_body_mppi.cpp:
+        246-262): R = |v / w| -- inf for w = 0, NaN for v = w = 0, exactly as the reference computes it."""
+        with np.errstate(divide="ignore", invalid="ignore"):
+            R = np.abs(np.float64(v) / np.float64(w))
+            s_in = np.arctan2(R * np.sin(delta), R * np.cos(delta) - self.TREAD / 2.0)
+            s_out = np.arctan2(R * np.sin(delta), R * np.cos(delta) + self.TREAD / 2.0)
+        return (float(s_in), float(s_out)) if w > 0.0 else (float(s_out), float(s_in))
+
+    def cmd_pos(self, robot=0):
+        """What publish_CmdPos sends (ccv_dynamixel_msgs/CmdPoseByRadian): dict(steer_l, steer_r, fore, rear, roll).
+        DiffDriveMPPI: diff_drive_mppi.cpp:255-263."""
+        po = float(self.p["pitch_offset"])
+        return dict(steer_l=0.0, steer_r=0.0, fore=po, rear=po, roll=0.0)
+
 
 class DiffDriveMPPI(_MPPIBase):
     """class DiffDriveMPPI (diff_drive_mppi.h:52): unicycle, controls (v, w)."""
@@ -263,6 +280,13 @@ class SteeringDiffDriveMPPI(_MPPIBase):
     """class SteeringDiffDriveMPPI (steering_diff_drive_mppi.h:56): controls (v, w, steer)."""
     MODEL = "steering"
 
+    def cmd_pos(self, robot=0):
+        """steering_diff_drive_mppi.cpp:273-296"""
+        u = self.optimal_solution[robot, 0]
+        l, r = self._steer_in_out(u[0], u[1], u[2])
+        po = float(self.p["pitch_offset"])
+        return dict(steer_l=l, steer_r=r, fore=po, rear=po, roll=0.0)
+
 
 class FullBodyMPPI(_MPPIBase):
     """class FullBodyMPPI (full_body_mppi.h:68): controls (v, w, direction, roll_v, pitch_v), ZMP cost."""
@@ -272,6 +296,21 @@ class FullBodyMPPI(_MPPIBase):
     MASS, BODY_H, BODY_D, BODY_W, ALPHA = 60.0, 0.8075, 0.208, 0.208, 0.3  # full_body_mppi.h:213-218
     CONTACTS = np.array([[0.0, 0.225, 0.075], [0.0, -0.225, 0.075], [0.245, 0.167, -0.003], [0.245, -0.167, -0.004],
                          [-0.245, -0.167, -0.004], [-0.245, 0.167, -0.003]])  # full_body_mppi.cpp:57-63
+
+    def cmd_pos(self, robot=0):
+        """full_body_mppi.cpp:246-275: steer_off zeroes the steering, the roll command is the current roll advanced by
+        roll_v[0] * dt, clamped to [roll_min, roll_max], and zeroed by roll_off."""
+        u = self.optimal_solution[robot, 0]
+        l, r = (0.0, 0.0) if self.p.get("steer_off", False) else self._steer_in_out(u[0], u[1], u[2])
+        roll = float(self.current_state[robot, 3] + u[3] * self.dt_)
+        if roll > self.p["roll_max"]:
+            roll = float(self.p["roll_max"])
+        elif roll < self.p["roll_min"]:
+            roll = float(self.p["roll_min"])
+        if self.p.get("roll_off", False):
+            roll = 0.0
+        po = float(self.p["pitch_offset"])
+        return dict(steer_l=l, steer_r=r, fore=po, rear=po, roll=roll)
 
     def reset_monitors(self):
         self.zmp_x_, self.zmp_y_ = 0.0, 0.0

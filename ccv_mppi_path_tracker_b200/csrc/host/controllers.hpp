@@ -127,11 +127,18 @@ class MPPIBase {
     mppi_params p = abi_params();
     int rc = mppi_create(&h_, model_, &p, (int)num_samples_, horizon_, n_robots, device);
     if (rc != MPPI_OK) throw Error(rc, mppi_last_error(nullptr));
+    resize_host();
+  }
+  // the host-side members alone (optimal_solution zeroed like RobotStates::init, current state): what cmd_vel(),
+  // cmd_pos() and optimal_path() work on.  init() calls it; host-only tools call it instead of init().
+  void resize_host() {
     optimal_solution.horizon = horizon_;
     optimal_solution.U = U_;
-    optimal_solution.u.assign((size_t)(horizon_ - 1) * U_, 0.0);  // RobotStates::init zeroes the controls
+    optimal_solution.u.assign((size_t)(horizon_ - 1) * U_, 0.0);
     state_.assign(S_, 0.0);
   }
+  // the mppi_params the class hands to the C ABI (parity checks)
+  mppi_params params_for_abi() const { return abi_params(); }
   void update_params() { mppi_params p = abi_params(); check(mppi_set_params(h_, &p)); }
 
   // pathCallback (DD:48-52)

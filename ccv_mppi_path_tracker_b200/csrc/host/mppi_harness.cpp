@@ -3,8 +3,13 @@
 //
 //   mppi_harness --model dd|sd|fb [--K n] [--T n] [--cycles n] [--path file.csv | --sin L A1 omega1] [--launch]
 //                [--param name=value ...] [--seed s] [--graph] [--split] [--quiet]
+//                [--state x,y,yaw[,roll,pitch]] [--noise eps.f32] [--u0 u.f64] [--dump out.bin]
 // Prints one line per cycle (pose, cmd_vel, cmd_pos) and a JSON summary with the solve latency percentiles and
 // the cross-track RMSE against the path (the metric of the reference's src/calc_e_rmse.py:30-49).
+// Parity mode (tests/test_gpu_parity.py): --noise feeds a standard-normal tensor [T-1][K][U] (float32, the reference's
+// draw order) instead of the internal generator, --u0 a warm start [T-1][U] (float64), --state the initial pose;
+// --dump writes, after the FIRST cycle, the mppi_params the class handed to the C ABI (raw struct), the new
+// optimal_solution [T-1][U] (float64) and the per-sample costs [K] (float32).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -21,7 +26,7 @@ static double nearest_path_distance(const std::vector<double> &xy, double x, dou
 }
 
 int main(int argc, char **argv) {
-  std::string model = "dd", path_file;
+  std::string model = "dd", path_file, noise_file, u0_file, dump_file, state_arg;
   int K = -1, T = -1, cycles = 50;
   bool launch = false, graph = false, split = false, quiet = false;
   double L = 10.0, A1 = 1.0, om1 = 0.25;
@@ -41,6 +46,10 @@ int main(int argc, char **argv) {
     else if (s == "--split") split = true;
     else if (s == "--quiet") quiet = true;
     else if (s == "--seed") seed = strtoull(next(), nullptr, 0);
+    else if (s == "--noise") noise_file = next();
+    else if (s == "--u0") u0_file = next();
+    else if (s == "--dump") dump_file = next();
+    else if (s == "--state") state_arg = next();
     else if (s == "--param") {
       std::string kv = next();
       size_t eq = kv.find('=');
@@ -80,6 +89,27 @@ int main(int argc, char **argv) {
     ctl->pathCallback(path);
 
     double x = path[0], y = path[1], yaw = 0.0, roll = 0.0, pitch = 0.0;
+    if (!state_arg.empty()) {
+      double v[5] = {x, y, 0, 0, 0};
+      int k = 0;
+      std::stringstream ss(state_arg);
+      std::string tok;
+      while (k < 5 && std::getline(ss, tok, ',')) v[k++] = atof(tok.c_str());
+      x = v[0]; y = v[1]; yaw = v[2]; roll = v[3]; pitch = v[4];
+    }
+    auto read_file = [](const std::string &name, size_t bytes, void *dst) {
+      FILE *f = fopen(name.c_str(), "rb");
+      if (!f || fread(dst, 1, bytes, f) != bytes) throw Error(MPPI_ERR_INVALID, "cannot read " + name);
+      fclose(f);
+    };
+    const size_t n_u = (size_t)(ctl->horizon_ - 1) * ctl->num_controls();
+    if (!noise_file.empty()) {
+      std::vector<float> eps(n_u * (size_t)ctl->num_samples_);
+      read_file(noise_file, eps.size() * sizeof(float), eps.data());
+      int rc = mppi_set_noise(ctl->handle(), eps.data());
+      if (rc != MPPI_OK) throw Error(rc, mppi_last_error(ctl->handle()));
+    }
+    if (!u0_file.empty()) read_file(u0_file, n_u * sizeof(double), ctl->optimal_solution.u.data());
     std::vector<double> lat_us;
     double se = 0.0, emax = 0.0;
     for (int c = 0; c < cycles; ++c) {
@@ -91,6 +121,16 @@ int main(int argc, char **argv) {
       else ctl->solve();
       auto t1 = std::chrono::steady_clock::now();
       lat_us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+      if (c == 0 && !dump_file.empty()) {
+        FILE *o = fopen(dump_file.c_str(), "wb");
+        if (!o) throw Error(MPPI_ERR_INVALID, "cannot write " + dump_file);
+        const mppi_params p = ctl->params_for_abi();
+        const std::vector<float> cost = ctl->costs();
+        fwrite(&p, sizeof p, 1, o);
+        fwrite(ctl->optimal_solution.u.data(), sizeof(double), ctl->optimal_solution.u.size(), o);
+        fwrite(cost.data(), sizeof(float), cost.size(), o);
+        fclose(o);
+      }
       const CmdVel cv = ctl->cmd_vel();
       const CmdPos cp = ctl->cmd_pos();
       const ControlSequence &u = ctl->optimal_solution;

@@ -94,3 +94,17 @@ def run_estimator(cycles):
         subprocess.run([os.path.join(_HERE, "_ref", BIN["full_body"]), "--estimator", fin, fout], check=True,
                        stderr=subprocess.DEVNULL)
         return np.fromfile(fout, dtype=np.float64).reshape(-1, 5)
+
+
+def run_cmd(model, cases):
+    """cases: [n][8] doubles {v0, w0, steer0 / direction0, roll_v0, roll_state, dt, steer_off, roll_off}; returns [n][7]
+    {cmd_vel.linear.x, cmd_vel.angular.z, steer_l, steer_r, fore, rear, roll} from the reference's own
+    publish_CmdVel() + publish_CmdPos() (default constructor parameters)."""
+    cases = np.ascontiguousarray(cases, dtype=np.float64).reshape(-1, 8)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<i", cases.shape[0]))
+            f.write(cases.tobytes())
+        subprocess.run([os.path.join(_HERE, "_ref", BIN[model]), "--cmd", fin, fout], check=True, stderr=subprocess.DEVNULL)
+        return np.fromfile(fout, dtype=np.float64).reshape(-1, 7)

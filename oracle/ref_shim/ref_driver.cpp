@@ -135,9 +135,55 @@ static int run_estimator(const char *fin, const char *fout) {
 }
 #endif
 
+// command mode: argv = --cmd in out.  in: int32 n, then per case 8 doubles {v0, w0, steer0 (SD) / direction0 (FB),
+// roll_v0, roll of the current state, dt, steer_off, roll_off}; out: per case 7 doubles {cmd_vel.linear.x,
+// cmd_vel.angular.z, cmd_pos.steer_l, steer_r, fore, rear, roll} as the reference's own publish_CmdVel() and
+// publish_CmdPos() leave them in the message members (DD:248-263, SD:266-296, FB:238-275).
+static int run_cmd(const char *fin, const char *fout) {
+  FILE *f = fopen(fin, "rb");
+  if (!f) return 1;
+  int32_t n;
+  rd(f, &n, 1);
+  std::vector<double> in((size_t)n * 8);
+  rd(f, in.data(), in.size());
+  fclose(f);
+  std::cout.setstate(std::ios_base::failbit);
+  ref_shim::param_table()["horizon"] = 3;
+  ref_shim::param_table()["num_samples"] = 1;
+  Node node;
+  FILE *o = fopen(fout, "wb");
+  for (int c = 0; c < n; ++c) {
+    const double *v = in.data() + (size_t)c * 8;
+#if REF_NODE == 3
+    RobotStates &opt = node.optimal_solution_;
+    opt.direction_[0] = v[2];
+    opt.roll_v_[0] = v[3];
+    node.current_state_.roll_[0] = v[4];
+    node.steer_off_ = v[6] != 0.0;
+    node.roll_off_ = v[7] != 0.0;
+#else
+    RobotStates &opt = node.optimal_solution;
+#if REF_NODE == 2
+    opt.steer_[0] = v[2];
+#endif
+#endif
+    opt.v_[0] = v[0];
+    opt.w_[0] = v[1];
+    node.dt_ = v[5];
+    node.publish_CmdVel();
+    node.publish_CmdPos();
+    double out[7] = {node.cmd_vel_.linear.x, node.cmd_vel_.angular.z, node.cmd_pos_.steer_l, node.cmd_pos_.steer_r,
+                     node.cmd_pos_.fore,     node.cmd_pos_.rear,      node.cmd_pos_.roll};
+    fwrite(out, 8, 7, o);
+  }
+  fclose(o);
+  return 0;
+}
+
 #include <chrono>
 
 int main(int argc, char **argv) {
+  if (argc >= 4 && std::string(argv[1]) == "--cmd") return run_cmd(argv[2], argv[3]);
 #if REF_NODE == 3
   if (argc >= 4 && std::string(argv[1]) == "--estimator") return run_estimator(argv[2], argv[3]);
 #endif

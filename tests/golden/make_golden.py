@@ -60,6 +60,34 @@ def main():
         print(name, "cost range", r["cost"].min(), r["cost"].max(), "u_new[0]", r["u_new"][0])
 
 
+def cmd_golden():
+    """publish_CmdVel + publish_CmdPos of the three nodes (DD:248-263, SD:266-296, FB:238-275) for first controls that
+    cover both turning directions, w = 0 (R = inf), v = w = 0 (R = NaN), the roll clamp, steer_off and roll_off."""
+    rng = np.random.default_rng(55)
+    n = 40
+    c = np.zeros((n, 8))
+    c[:, 0] = rng.uniform(-1.0, 2.0, n)                  # v0
+    c[:, 1] = rng.uniform(-1.0, 1.0, n)                  # w0
+    c[:, 2] = rng.uniform(-0.52, 0.52, n)                # steer0 / direction0
+    c[:, 3] = rng.uniform(-0.6, 0.6, n)                  # roll_v0
+    c[:, 4] = rng.uniform(-0.6, 0.6, n)                  # roll of the current state (beyond +-30 deg in places)
+    c[:, 5] = rng.uniform(0.08, 0.12, n)                 # dt
+    c[0, 1] = 0.0                                        # w = 0: R = inf
+    c[1, 0], c[1, 1] = 0.0, 0.0                          # v = w = 0: R = NaN
+    c[2, 1], c[2, 2] = 0.0, 0.0                          # w = 0 and steer = 0: inf * 0
+    c[3, 1] = -0.0
+    c[4, 3], c[4, 4] = 3.0, 0.5                          # roll command far beyond roll_max
+    c[5, 3], c[5, 4] = -3.0, -0.5
+    c[6:12, 6] = 1.0                                     # steer_off
+    c[10:16, 7] = 1.0                                    # roll_off
+    out = {}
+    for model, tag in (("diff_drive", "dd"), ("steering", "sd"), ("full_body", "fb")):
+        out["ref_" + tag] = ref_runner.run_cmd(model, c)
+    np.savez_compressed(os.path.join(HERE, "cmd_golden.npz.dat"), cases=c, **out)
+    os.replace(os.path.join(HERE, "cmd_golden.npz.dat.npz"), os.path.join(HERE, "cmd_golden.dat"))
+    print("cmd_golden", {k: v[0] for k, v in out.items()})
+
+
 def estimator_golden():
     """Eight cycles of the full-body node's ZMP monitors (calc_true_ZMP + get_CurrentState, FB:528-596)."""
     rng = np.random.default_rng(77)
@@ -82,4 +110,5 @@ def estimator_golden():
 
 if __name__ == "__main__":
     estimator_golden()
+    cmd_golden()
     main()

@@ -179,3 +179,62 @@ def test_full_body_zmp_monitors_match_the_reference(tmp_path):
     subprocess.run([exe, str(fin), str(fout)], check=True)
     cpp = np.fromfile(fout, dtype=np.float64).reshape(-1, 5)
     assert np.allclose(cpp, ref, rtol=1e-12, atol=1e-15)
+
+
+def test_cmd_vel_and_cmd_pos_match_the_reference(tmp_path):
+    """f2: what publish_CmdVel / publish_CmdPos of the three UNMODIFIED reference nodes publish (golden cases incl.
+    w = 0 -> R = inf, v = w = 0 -> R = NaN, the w > 0 left/right swap, the roll clamp, steer_off and roll_off;
+    diff_drive_mppi.cpp:248-263, steering_diff_drive_mppi.cpp:266-296, full_body_mppi.cpp:238-275) against cmd_vel() /
+    cmd_pos() of the C++ host classes (bit for bit) and of the Python mirror."""
+    import struct
+    import subprocess
+    from ccv_mppi_path_tracker_b200 import controllers
+    from common import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "cmd_golden.dat"), allow_pickle=False)
+    cases = g["cases"]
+    # the golden covers the special cases it claims
+    assert cases[0, 1] == 0.0 and np.isnan(g["ref_sd"][1, 2]) and (cases[:, 6] == 1).any() and (cases[:, 7] == 1).any()
+    assert (g["ref_fb"][:, 6] == np.deg2rad(30.0)).any() and (g["ref_fb"][:, 6] == -np.deg2rad(30.0)).any()
+    exe = os.path.join(ROOT, "tests", "host", "cmd_check")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", ROOT, "hosttest"], check=True)
+    fin = tmp_path / "in.bin"
+    fin.write_bytes(struct.pack("<i", cases.shape[0]) + np.ascontiguousarray(cases).tobytes())
+    for tag, model in (("dd", "diff_drive"), ("sd", "steering"), ("fb", "full_body")):
+        ref = g["ref_" + tag]
+        fout = tmp_path / f"out_{tag}.bin"
+        subprocess.run([exe, tag, str(fin), str(fout)], check=True)
+        cpp = np.fromfile(fout, dtype=np.float64).reshape(-1, 7)
+        assert np.array_equal(cpp, ref, equal_nan=True), tag
+        # Python mirror: no device handle needed for the command post-processing
+        cls = controllers.CONTROLLERS[model]
+        ctl = cls.__new__(cls)
+        ctl.p = params.node_params(model, launch=False)
+        U, S = params.NUM_CONTROLS[model], params.NUM_STATES[model]
+        ctl.optimal_solution = np.zeros((1, 2, U))
+        ctl.current_state = np.zeros((1, S))
+        got = []
+        for v in cases:
+            ctl.optimal_solution[0, 0, :2] = v[:2]
+            if U > 2:
+                ctl.optimal_solution[0, 0, 2] = v[2]
+            ctl.dt_ = v[5]
+            if model == "full_body":
+                ctl.optimal_solution[0, 0, 3] = v[3]
+                ctl.current_state[0, 3] = v[4]
+                ctl.p["steer_off"], ctl.p["roll_off"] = bool(v[6]), bool(v[7])
+            cv, cp = ctl.cmd_vel(), ctl.cmd_pos()
+            got.append([cv[0], cv[1], cp["steer_l"], cp["steer_r"], cp["fore"], cp["rear"], cp["roll"]])
+        assert np.allclose(np.array(got), ref, rtol=1e-14, atol=1e-16, equal_nan=True), tag
+
+
+def test_circle_path_generator():
+    """reference_path_creator.cpp:57-68: the circle course (its step formula `resolution / 2 * pi * R` kept as is)."""
+    p = paths.circle_path(R=2.0, resolution=0.1, init_x=1.0, init_y=-0.5)
+    step = 0.1 / 2 * np.pi * 2.0
+    n = int(np.floor(200 * np.pi / step)) + 1
+    assert p.shape == (n, 2) or p.shape == (n + 1, 2)  # accumulated `s += step` may land a hair below the bound
+    s = np.arange(p.shape[0]) * step
+    assert np.allclose(p[:, 0], 1.0 + 2.0 * np.cos(s), atol=1e-9) and np.allclose(p[:, 1], -0.5 + 2.0 * np.sin(s) + 2.0, atol=1e-9)
+    assert np.allclose(np.hypot(p[:, 0] - 1.0, p[:, 1] - 1.5), 2.0)
+    assert np.array_equal(p[0], [3.0, 1.5])

@@ -994,3 +994,47 @@ def test_device_resident_warm_start_equals_the_uploaded_one(R, graph):
     assert 0 <= io[1][0] - io[0][0] - 4 * R * planes < 16  # the warm start (+ alignment) is what no longer travels
     if R >= 8:  # device-built windows: header + FP64 pose + state record per robot
         assert io[0][0] == 256 + R * (16 + 16)
+
+
+@pytest.mark.parametrize("tag,model,extra", [("dd", "diff_drive", {}), ("sd", "steering", {"steer_max": 0.4}),
+                                             ("fb", "full_body", {"roll_off": 0.0, "zmp_weight": 7.0})])
+def test_cpp_host_classes_hand_the_reference_parameters_to_the_abi(tag, model, extra, tmp_path):
+    """The C++ host classes (csrc/host/controllers.hpp) are what a node maintainer links: one solve from
+    `mppi_harness --launch` with a fed noise tensor must (a) hand the C ABI the same mppi_params as the Python mirror
+    builds from the same ROS parameters and (b) match the FP64 oracle -- pinning the C++ parameter mapping
+    (abi_params(): control_weight quirk, roll_off zeroing the ZMP weights, launch-file overrides) like the Python one."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "ccv_mppi_path_tracker_b200", "mppi_harness")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", root, "harness"], check=True)
+    K, T = 1536, 40
+    ov = {k: (bool(v) if k in ("roll_off", "steer_off") else v) for k, v in extra.items()}
+    if model == "full_body" and "roll_off" not in ov:
+        ov["roll_off"] = True
+    case = make_case(model, K, T, seed=43, **ov)
+    eps_f, u0_f, dump_f = tmp_path / "eps.f32", tmp_path / "u0.f64", tmp_path / "dump.bin"
+    case["eps"].astype(np.float32).tofile(eps_f)
+    case["u0"].astype(np.float64).tofile(u0_f)
+    args = [exe, "--model", tag, "--launch", "--K", str(K), "--T", str(T), "--cycles", "1", "--quiet",
+            "--state", ",".join(repr(float(v)) for v in case["state"]), "--noise", str(eps_f), "--u0", str(u0_f),
+            "--dump", str(dump_f)]
+    for k, v in extra.items():
+        args += ["--param", f"{k}={v}"]
+    subprocess.run(args, check=True, capture_output=True)
+    raw = open(dump_f, "rb").read()
+    p_cpp = _capi.MppiParams.from_buffer_copy(raw[:C.sizeof(_capi.MppiParams)])
+    off = C.sizeof(_capi.MppiParams)
+    U = case["U"]
+    u_cpp = np.frombuffer(raw, dtype=np.float64, count=(T - 1) * U, offset=off).reshape(T - 1, U)
+    cost_cpp = np.frombuffer(raw, dtype=np.float32, count=K, offset=off + 8 * (T - 1) * U)
+    sp = case["sp"]
+    for name in ("control_noise", "lambda_", "v_ref", "resolution", "path_weight", "v_weight", "zmp_weight", "roll_v_weight",
+                 "back_weight", "yaw_weight", "steer_off"):
+        assert getattr(p_cpp, name) == sp[name], name
+    assert list(p_cpp.u_min)[:U] == sp["u_min"][:U] and list(p_cpp.u_max)[:U] == sp["u_max"][:U]
+    o = oracle.solve(model, sp, K, T, case["state"], case["dt"], case["path"], case["eps"], case["u0"])
+    assert np.all(np.abs(cost_cpp - o["cost"]) <= COST_RTOL * np.abs(o["cost"]) + COST_ATOL)
+    assert (np.abs(u_cpp - o["u_new"]) / _urange(case)).max() <= U_TOL
