@@ -625,7 +625,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   const int nb3_weights = d.nb3;  // blocks of the stand-alone weight kernel (also the on-demand weights tap)
   if (fused_weights(h)) d.nb3 = d.nchunk;  // the partial (sum w, sum w^2) come from K4's chunks
   CU_NEW(cudaMalloc((void **)&d.wpart, sizeof(float) * (size_t)d.R * (nb3_weights > d.nb3 ? nb3_weights : d.nb3) * 2));
-  CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.planes * d.nchunk));
+  // K4's per-chunk partial numerators [R][P][nchunk]; the one-kernel tail keeps its per-group partial records
+  // [R][groups <= nchunk][rec_stride] here
+  CU_NEW(cudaMalloc((void **)&d.npart, sizeof(float) * (size_t)d.R * d.rec_stride * d.nchunk));
   CU_NEW(cudaMalloc((void **)&d.record, sizeof(float) * (size_t)d.R * d.rec_stride));
   // per-CTA records of the fused weighted controls (fused_controls() decides per solve whether K2 writes them)
   CU_NEW(cudaMalloc((void **)&d.cta_part, sizeof(float) * (size_t)d.R * ((d.K + 127) / 128) * d.rec_stride));

@@ -103,6 +103,11 @@ __host__ __device__ __forceinline__ uint32_t cell_entry(int first_pair, int iter
 // min over the window pairs of one cell entry of min(d2, 1e4); pairs = {x0, x1, y0, y1}.  Two pairs (four window
 // points) per iteration, at least one iteration; scanning a few points more than the candidate range is always
 // safe (they are window points too), so the range is rounded up instead of predicated.
+// (Round 2 tried to hand the rare long ranges -- ~0.7 % of the states, but they set the iteration count of ~18 % of
+// the warp-steps -- to the whole warp: owner's position and range broadcast by shuffles, one pair per lane, shuffle-tree
+// minimum.  Bit-identical, but a loss wherever several lanes of a warp are long at once (coarse grids, states outside
+// the grid): K2 20 -> 32 us at K = 4096 / T = 50, 240 -> 505 us for 1024 robots, +-2 % at K = 2^17 .. 2^20.  Dropped;
+// numbers in DESIGN.md section 4.)
 __device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float x, float y) {
   const u64 xx = pack2(x, x), yy = pack2(y, y);
   unsigned p = pairs_s + (e & 0xFFFFu);
@@ -636,7 +641,8 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float 
   const bool steer_off = MODEL == kFullBody && sP.steer_off;
   // a warp takes 4 consecutive planes at a time: 4 independent 16-byte loads per lane, then one transposing butterfly
   // reduces the 4 partial sums over the 32 lanes (lanes 0, 8, 16, 24 end up with one plane each); fixed order,
-  // deterministic.  (8 planes at a time would cost the kernel 18 more registers and two resident CTAs per SM.)
+  // deterministic.  (Issuing the next four planes' loads ahead of the arithmetic, or 8 planes at a time, costs 12-18
+  // registers -- one resident CTA per SM -- and gained nothing at K = 2^17 .. 2^20: measured, dropped.)
   for (int p0 = wid * 4; p0 < planes; p0 += 16) {
     float4 e[4];
 #pragma unroll
@@ -683,11 +689,17 @@ size_t pruned_tma_smem_bytes(int T, int planes, int U) {
          sizeof(float) * ((size_t)planes + 2 * U);
 }
 
+// resident CTAs per SM the register allocation must allow: 9 (56 registers) for the two- and three-control models --
+// what the rollout loop needs anyway; the bound only keeps the rare-path code of the scan from raising it -- and 5
+// for the full-body model
 #ifndef MPPI_K2_MINBLOCKS
-#define MPPI_K2_MINBLOCKS 1
+#define MPPI_K2_MINBLOCKS 9
+#endif
+#ifndef MPPI_K2_MINBLOCKS_FB
+#define MPPI_K2_MINBLOCKS_FB 5
 #endif
 template <int MODEL, bool TAP>
-__global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
+__global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB : MPPI_K2_MINBLOCKS)
     rollout_cost_tma_kernel(const __grid_constant__ CUtensorMap eps_map, const __grid_constant__ ControlBounds kb,
                             const SolveHeader *__restrict__ hdr,
                             const float *__restrict__ nominal, const float *__restrict__ window,
@@ -764,191 +776,145 @@ __global__ void __launch_bounds__(128, MPPI_K2_MINBLOCKS)
                                cta_part + ((size_t)robot * gridDim.x + blockIdx.x) * part_stride);
 }
 
-// ---- K3': rescale of the per-CTA records ------------------------------------------------------------------------
-// Brings the records of K2's CTAs to the robot's global minimum and folds them into partial sums:
-//   a_c = exp(-(m_c - c_min)/lambda);  wpart[g] = {sum_c a_c S_c, sum_c a_c^2 Q_c},  npart[g][p] = sum_c a_c N_c[p]
-// over the CTAs c of group g.  One block per (group, robot); thread = plane (coalesced over the records' rows),
-// kTailMlp independent accumulators per thread keep as many loads in flight (the tail is a chain of L2 round trips,
-// not bandwidth) and are combined in a fixed order (deterministic).
+// ---- the tail of the fused-controls path: K3' + K5 + K6 (+ the record exchange) in ONE launch ---------------------
+// K2 left one record {m_c, S_c, Q_c, -, N_c[P]} per CTA, exponentiated against the CTA's own minimum m_c.  With
+//   a_c = exp(-(m_c - c_min)/lambda):   S = sum_c a_c S_c,   Q = sum_c a_c^2 Q_c,   N[p] = sum_c a_c N_c[p]
+// the robot's record {c_min, S, Q, -, N[P]} follows column by column: one thread per record column, the same loop for
+// every column (weight a_c, or a_c^2 for the Q column), coalesced over the records' rows.  The tail is a chain of L2
+// round trips, not bandwidth, so it is kept to two: every block folds its group of CTA records (all loads of a thread
+// -- the CTA minima, broadcast, and its column -- are independent: one batch), the block that finishes last for a robot
+// adds the groups' partial records (a second batch) and, MODE 0 (unsharded), merges: u = N / S -> u_new, warm start,
+// stats.  The block that finishes last of the whole grid advances the solve counter and, MODE 1 (peer exchange),
+// first runs exchange_and_merge for all robots.  MODE 2: records only (NCCL all-gather + merge kernel follow).
+// Sums use kTailMlp interleaved accumulators combined in a fixed order: deterministic for a given launch geometry.
 constexpr int kTailMlp = 32;
-__device__ __forceinline__ float sum_fixed(const float (&a)[kTailMlp]) {
-  float s[kTailMlp / 2];
+template <int B>
+__device__ __forceinline__ float sum_fixed(const float (&a)[B]) {
+  float s[B / 2];
 #pragma unroll
-  for (int k = 0; k < kTailMlp / 2; ++k) s[k] = a[2 * k] + a[2 * k + 1];
+  for (int k = 0; k < B / 2; ++k) s[k] = a[2 * k] + a[2 * k + 1];
 #pragma unroll
-  for (int w = kTailMlp / 4; w > 0; w >>= 1)
+  for (int w = B / 4; w > 0; w >>= 1)
 #pragma unroll
     for (int k = 0; k < w; ++k) s[k] = s[2 * k] + s[2 * k + 1];
   return s[0];
 }
-__device__ __forceinline__ void rescale_group(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
-                                              const unsigned int *__restrict__ cmin, float *__restrict__ wpart,
-                                              float *__restrict__ npart, int planes, int n_cta, int part_stride,
-                                              int groups, int per, int robot, int g, float *s_a) {
-  const int c0 = g * per, c1 = min(c0 + per, n_cta), nc = c1 - c0;
-  const float c_min = ordered_to_float(cmin[robot]);
-  const float inv_lambda = hdr->inv_lambda;
-  const float *part = cta_part + ((size_t)robot * n_cta + c0) * part_stride;
-  for (int c = threadIdx.x; c < kRescaleMaxCtas; c += blockDim.x)  // padded with zeros: no tail code below
-    s_a[c] = c < nc ? expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda) : 0.f;
-  __syncthreads();
-  const int ncm = (nc + kTailMlp - 1) / kTailMlp * kTailMlp;  // <= kRescaleMaxCtas (a multiple of kTailMlp)
-  for (int p = threadIdx.x; p < planes; p += blockDim.x) {
-    float acc[kTailMlp];
+
+// column `col` of the rescaled sum over nc CTA records of one robot (col 1: S, col 2: Q, col >= 4: N[col - 4]);
+// B loads of the minima + B loads of the column in flight per thread
+template <int B>
+__device__ __forceinline__ float fold_records(const float *__restrict__ part, int part_stride, int nc, int col,
+                                              float c_min, float inv_lambda) {
+  float acc[B];
 #pragma unroll
-    for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
-    for (int c = 0; c < ncm; c += kTailMlp) {
-      float v[kTailMlp];
+  for (int k = 0; k < B; ++k) acc[k] = 0.f;
+  for (int c = 0; c < nc; c += B) {
+    float m[B], v[B];
 #pragma unroll
-      for (int k = 0; k < kTailMlp; ++k)
-        v[k] = part[(size_t)min(c + k, nc - 1) * part_stride + 4 + p];  // weight 0 past the end
-#pragma unroll
-      for (int k = 0; k < kTailMlp; ++k) acc[k] = fmaf(s_a[c + k], v[k], acc[k]);
+    for (int k = 0; k < B; ++k) {
+      const float *rec = part + (size_t)min(c + k, nc - 1) * part_stride;
+      m[k] = rec[0];  // the same address for every thread of the block: one broadcast request
+      v[k] = rec[col];
     }
-    npart[((size_t)robot * groups + g) * planes + p] = sum_fixed(acc);
-  }
-  if (threadIdx.x < 32) {  // warp 0: S and Q of the group, lanes stride over the CTAs, fixed shuffle tree
-    float S = 0.f, Q = 0.f;
-    for (int c = threadIdx.x; c < nc; c += 32) {
-      const float a = s_a[c];
-      S = fmaf(a, part[(size_t)c * part_stride + 1], S);
-      Q = fmaf(a * a, part[(size_t)c * part_stride + 2], Q);
-    }
-    S = warp_sum(S);
-    Q = warp_sum(Q);
-    if (threadIdx.x == 0) {
-      wpart[((size_t)robot * groups + g) * 2] = S;
-      wpart[((size_t)robot * groups + g) * 2 + 1] = Q;
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      float a = c + k < nc ? expf(-(m[k] - c_min) * inv_lambda) : 0.f;
+      if (col == 2) a *= a;
+      acc[k] = fmaf(a, v[k], acc[k]);
     }
   }
+  return sum_fixed<B>(acc);
 }
 
-// ---- the whole tail in one launch (fused-controls path) ----------------------------------------------------------
-// grid = (groups, robots).  Every block rescales its group (above); the block that finishes last for a robot sums the
-// groups in fixed order into the robot's record {c_min, S, Q, -, N[P]} and, MODE 0 (unsharded), merges it: u = N / S ->
-// u_new, warm start, stats.  The block that finishes last of the whole grid advances the solve counter and, MODE 1
-// (peer exchange), first runs exchange_and_merge for all robots.  MODE 2: records only (NCCL all-gather + merge follow).
 template <int MODE>
 __global__ void __launch_bounds__(256)
     rescale_tail_kernel(const SolveHeader *__restrict__ hdr, const float *__restrict__ cta_part,
-                        unsigned int *__restrict__ cmin, float *__restrict__ wpart, float *__restrict__ npart,
-                        float *__restrict__ record, float *__restrict__ u_new, float *__restrict__ nominal,
-                        float *__restrict__ stats, uint32_t *__restrict__ counter, unsigned int *__restrict__ ticket,
-                        int planes, int n_cta, int part_stride, int groups, int per, int R, ExchangeArgs x) {
-  __shared__ float s_a[kRescaleMaxCtas];
+                        unsigned int *__restrict__ cmin, float *__restrict__ gpart, float *__restrict__ record,
+                        float *__restrict__ u_new, float *__restrict__ nominal, float *__restrict__ stats,
+                        uint32_t *__restrict__ counter, unsigned int *__restrict__ ticket, int planes, int n_cta,
+                        int part_stride, int groups, int per, int R, ExchangeArgs x) {
   __shared__ float s_S;
-  const int robot = blockIdx.y;
-  if (groups == 1 && MODE == 0) {
-    // Many-robot handles: one block owns the robot -- rescale, record and merge without leaving the block (no
-    // tickets, no fences, no partial arrays).  Same arithmetic and summation order as the general path below.
-    const float c_min = ordered_to_float(cmin[robot]);
-    const float inv_lambda = hdr->inv_lambda;
-    const float *part = cta_part + (size_t)robot * n_cta * part_stride;
-    for (int c = threadIdx.x; c < kRescaleMaxCtas; c += blockDim.x)
-      s_a[c] = c < n_cta ? expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda) : 0.f;
-    __syncthreads();
-    float *rec = record + (size_t)robot * part_stride;
-    if (threadIdx.x < 32) {
-      float S = 0.f, Q = 0.f;
-      for (int c = threadIdx.x; c < n_cta; c += 32) {
-        const float a = s_a[c];
-        S = fmaf(a, part[(size_t)c * part_stride + 1], S);
-        Q = fmaf(a * a, part[(size_t)c * part_stride + 2], Q);
-      }
-      S = warp_sum(S);
-      Q = warp_sum(Q);
-      if (threadIdx.x == 0) {
-        cmin[robot] = 0xFFFFFFFFu;  // re-armed for the next solve (every reader of this block is past the barrier)
-        rec[0] = c_min;
-        rec[1] = S;
-        rec[2] = Q;
-        rec[3] = 0.f;
-        const float Sm = fmaf(1.f, S, 0.f), Qm = fmaf(1.f, Q, 0.f);  // merge_sums with one rank
-        s_S = Sm;
-        stats[robot * 4 + 0] = c_min;
-        stats[robot * 4 + 1] = Sm;
-        stats[robot * 4 + 2] = Sm * Sm / Qm;
-        stats[robot * 4 + 3] = 0.f;
-        if (robot == 0) *counter = *counter + 1u;  // nothing reads it before the next solve's kernels
-      }
-    }
-    __syncthreads();
-    const float Sm = s_S;
-    const int ncm = (n_cta + kTailMlp - 1) / kTailMlp * kTailMlp;
-    for (int p = threadIdx.x; p < planes; p += blockDim.x) {
+  const int robot = blockIdx.y, g = blockIdx.x;
+  const int ncol = 4 + planes;
+  const float c_min = ordered_to_float(cmin[robot]);
+  const float inv_lambda = hdr->inv_lambda;
+  const int c0 = g * per, nc = min(per, n_cta - c0);
+  const float *part = cta_part + ((size_t)robot * n_cta + c0) * part_stride;
+  float *rec = record + (size_t)robot * part_stride;
+  // many-robot handles: one block owns the robot and (record columns <= 2 per thread) nothing leaves its registers
+  const bool in_regs = ncol <= 2 * (int)blockDim.x;
+  const bool single_regs = groups == 1 && in_regs;
+  float *gp = gpart + ((size_t)robot * groups + g) * part_stride;
+  float mine0 = 0.f, mine1 = 0.f;  // this thread's (up to two) columns
+  int slot = 0;
+  for (int col = threadIdx.x; col < ncol; col += blockDim.x, ++slot) {
+    float v = 0.f;
+    if (col != 0 && col != 3)
+      v = nc <= 8 ? fold_records<8>(part, part_stride, nc, col, c_min, inv_lambda)
+                  : fold_records<kTailMlp>(part, part_stride, nc, col, c_min, inv_lambda);
+    if (!single_regs) gp[col] = v;
+    else if (slot == 0) mine0 = v;
+    else mine1 = v;
+  }
+  if (!single_regs) {
+    if (!last_block_of_grid(ticket + 1 + robot, gridDim.x)) return;
+  } else {
+    __syncthreads();  // every thread has read cmin before it is re-armed below
+  }
+  // this block finishes the robot: add the groups' partial records, column by column
+  slot = 0;
+  for (int col = threadIdx.x; col < ncol; col += blockDim.x, ++slot) {
+    float tot;
+    if (single_regs) {
+      tot = slot == 0 ? mine0 : mine1;
+    } else {
+      const float *q = gpart + (size_t)robot * groups * part_stride + col;
       float acc[kTailMlp];
 #pragma unroll
       for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
-      for (int c = 0; c < ncm; c += kTailMlp) {
-        float v[kTailMlp];
+      for (int gg = 0; gg < groups; gg += kTailMlp) {
 #pragma unroll
-        for (int k = 0; k < kTailMlp; ++k) v[k] = part[(size_t)min(c + k, n_cta - 1) * part_stride + 4 + p];
-#pragma unroll
-        for (int k = 0; k < kTailMlp; ++k) acc[k] = fmaf(s_a[c + k], v[k], acc[k]);
+        for (int k = 0; k < kTailMlp; ++k)
+          acc[k] += gg + k < groups ? __ldcg(q + (size_t)(gg + k) * part_stride) : 0.f;  // written by other blocks
       }
-      const float a = sum_fixed(acc);
-      rec[4 + p] = a;
-      const float u = fmaf(1.f, a, 0.f) / Sm;  // merge_numerator with one rank
-      u_new[(size_t)robot * planes + p] = u;
-      if (nominal) nominal[(size_t)robot * planes + p] = u;
+      tot = sum_fixed<kTailMlp>(acc);
     }
-    return;
+    if (col == 0) tot = c_min;
+    rec[col] = tot;
+    if (col == 1) s_S = fmaf(1.f, tot, 0.f);  // merge_sums with one rank
+    if (slot == 0) mine0 = tot;
+    else if (slot == 1) mine1 = tot;
   }
-  rescale_group(hdr, cta_part, cmin, wpart, npart, planes, n_cta, part_stride, groups, per, robot, blockIdx.x, s_a);
-  if (!last_block_of_grid(ticket + 1 + robot, gridDim.x)) return;
-  // last block of this robot: fixed-order sums over the groups (__ldcg: written by other blocks of this launch)
-  float *rec = record + (size_t)robot * part_stride;
-  if (threadIdx.x < 32) {
-    const float *wp = wpart + (size_t)robot * groups * 2;
-    float a = 0.f, b = 0.f;
-    for (int g = threadIdx.x; g < groups; g += 32) {
-      a += __ldcg(wp + 2 * g);
-      b += __ldcg(wp + 2 * g + 1);
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (threadIdx.x == 0) {
-      const float m = ordered_to_float(cmin[robot]);
-      cmin[robot] = 0xFFFFFFFFu;  // every block of this robot has read it: ready for the next solve's atomicMin
-      rec[0] = m;
-      rec[1] = a;
-      rec[2] = b;
-      rec[3] = 0.f;
-      if (MODE == 0) {
-        const float S = fmaf(1.f, a, 0.f), Q = fmaf(1.f, b, 0.f);  // merge_sums with one rank
-        s_S = S;
-        stats[robot * 4 + 0] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) cmin[robot] = 0xFFFFFFFFu;  // every reader of this solve is done: armed for the next atomicMin
+  if (MODE == 0) {
+    const float S = s_S;
+    slot = 0;
+    for (int col = threadIdx.x; col < ncol; col += blockDim.x, ++slot) {
+      const float tot = in_regs ? (slot == 0 ? mine0 : mine1) : rec[col];
+      if (col >= 4) {
+        const float u = fmaf(1.f, tot, 0.f) / S;  // merge_numerator with one rank
+        u_new[(size_t)robot * planes + col - 4] = u;
+        if (nominal) nominal[(size_t)robot * planes + col - 4] = u;  // un-shifted warm start, as the reference (DD:89-90)
+      } else if (col == 2) {
+        const float Q = fmaf(1.f, tot, 0.f);
+        stats[robot * 4 + 0] = c_min;
         stats[robot * 4 + 1] = S;
         stats[robot * 4 + 2] = S * S / Q;
         stats[robot * 4 + 3] = 0.f;
       }
     }
+    // nothing reads the counter before the next solve's kernels: any one block may advance it
+    if (robot == 0 && threadIdx.x == 0) *counter = *counter + 1u;
+    return;
   }
-  __syncthreads();
-  const int gm = (groups + kTailMlp - 1) / kTailMlp * kTailMlp;
-  for (int p = threadIdx.x; p < planes; p += blockDim.x) {
-    const float *np = npart + (size_t)robot * groups * planes + p;
-    float acc[kTailMlp];
-#pragma unroll
-    for (int k = 0; k < kTailMlp; ++k) acc[k] = 0.f;
-    for (int g = 0; g < gm; g += kTailMlp) {
-#pragma unroll
-      for (int k = 0; k < kTailMlp; ++k) acc[k] += (g + k < groups) ? __ldcg(np + (size_t)(g + k) * planes) : 0.f;
-    }
-    const float a = sum_fixed(acc);
-    rec[4 + p] = a;
-    if (MODE == 0) {
-      const float u = fmaf(1.f, a, 0.f) / s_S;  // merge_numerator with one rank
-      u_new[(size_t)robot * planes + p] = u;
-      if (nominal) nominal[(size_t)robot * planes + p] = u;  // un-shifted warm start, as the reference (DD:89-90)
-    }
-  }
-  if (R > 1 && !last_block_of_grid(ticket, (unsigned)R)) return;
-  // last block of the solve
   if (MODE == 1) {
+    if (R > 1 && !last_block_of_grid(ticket, (unsigned)R)) return;
+    if (R == 1) {
+      __threadfence();
+      __syncthreads();
+    }
     exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R);
-  } else if (MODE == 0) {
-    if (threadIdx.x == 0) *counter = *counter + 1u;
   }
 }
 
@@ -971,9 +937,9 @@ cudaError_t launch_rescale_tail(const DeviceState &d, int mode, cudaStream_t s) 
   float *nominal = d.feedback ? d.nominal : nullptr;
   ExchangeArgs x = exchange_args(d);
 #define MPPI_LAUNCH_TAIL(M)                                                                                          \
-  rescale_tail_kernel<M><<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.wpart, d.npart, d.record, d.u_new, nominal, \
-                                              d.stats, d.counter, d.tail_ticket, d.planes, n_cta, d.rec_stride,      \
-                                              groups, per, d.R, x)
+  rescale_tail_kernel<M><<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.npart, d.record, d.u_new, nominal, d.stats, \
+                                              d.counter, d.tail_ticket, d.planes, n_cta, d.rec_stride, groups, per,  \
+                                              d.R, x)
   if (mode == 0) {
     MPPI_LAUNCH_TAIL(0);
   } else if (mode == 1) {
