@@ -78,16 +78,20 @@ __device__ __forceinline__ float *xchg_slot(void *base, int parity, int g, int G
 __device__ __forceinline__ void exchange_and_merge(const SolveHeader *__restrict__ hdr, const float *record,
                                                    const ExchangeArgs &x, float *__restrict__ u_new,
                                                    float *__restrict__ nominal, float *__restrict__ stats,
-                                                   uint32_t *__restrict__ counter, int planes, int rec_stride, int R) {
+                                                   uint32_t *__restrict__ counter, int planes, int rec_stride, int R,
+                                                   bool own_in_regs = false, float own0 = 0.f, float own1 = 0.f) {
   __shared__ int s_timeout;
   const int G = x.G;
   const unsigned int n = *x.seq;
   const int parity = (int)(n & 1u);
   const size_t slot_floats = (size_t)R * rec_stride;
   if (threadIdx.x == 0) s_timeout = 0;
-  for (int g = 0; g < G; ++g) {
-    float *dst = xchg_slot(x.peers[g], parity, x.rank, G, slot_floats);
-    for (size_t k = threadIdx.x; k < slot_floats; k += blockDim.x) dst[k] = __ldcg(record + k);
+  // every element is read once (or is still in the caller's registers: own_in_regs, one robot, <= 2 elements per
+  // thread) and stored to all G buffers: the stores are posted, nothing below depends on them before the fence
+  int slot = 0;
+  for (size_t k = threadIdx.x; k < slot_floats; k += blockDim.x, ++slot) {
+    const float v = own_in_regs ? (slot == 0 ? own0 : own1) : __ldcg(record + k);
+    for (int g = 0; g < G; ++g) xchg_slot(x.peers[g], parity, x.rank, G, slot_floats)[k] = v;
   }
   __threadfence_system();
   __syncthreads();

@@ -108,22 +108,39 @@ __host__ __device__ __forceinline__ uint32_t cell_entry(int first_pair, int iter
 // minimum.  Bit-identical, but a loss wherever several lanes of a warp are long at once (coarse grids, states outside
 // the grid): K2 20 -> 32 us at K = 4096 / T = 50, 240 -> 505 us for 1024 robots, +-2 % at K = 2^17 .. 2^20.  Dropped;
 // numbers in DESIGN.md section 4.)
-__device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float x, float y) {
-  const u64 xx = pack2(x, x), yy = pack2(y, y);
-  unsigned p = pairs_s + (e & 0xFFFFu);
-  const unsigned p_end = p + (e >> 16);
-  float best = kDist2Cap;
+__device__ __forceinline__ float pairs_min(float best, unsigned p, u64 xx, u64 yy) {  // two pairs at address p
+  const float4 a = lds128(p), b = lds128(p + 16u);
+  float a0, a1, b0, b1;
+  unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
+  unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
+  return min3f(min3f(best, a0, a1), b0, b1);
+}
+// first iteration of the scan: straight-line code (every range has at least one), so that the first iterations of
+// several states can be interleaved by the scheduler
+__device__ __forceinline__ float scan_first(unsigned pairs_s, uint32_t e, u64 xy) {
+  float x, y;
+  unpack2(xy, x, y);
+  return pairs_min(kDist2Cap, pairs_s + (e & 0xFFFFu), pack2(x, x), pack2(y, y));
+}
+// the rest of the range (~2 % of the states have one): the divergent part
+__device__ __forceinline__ float scan_rest(float best, unsigned pairs_s, uint32_t e, u64 xy) {
+  unsigned p = pairs_s + (e & 0xFFFFu) + 32u;
+  const unsigned p_end = p + (e >> 16) - 32u;
+  if (p != p_end) {
+    float x, y;
+    unpack2(xy, x, y);
+    const u64 xx = pack2(x, x), yy = pack2(y, y);
 #pragma unroll 1
-  do {
-    const float4 a = lds128(p), b = lds128(p + 16u);
-    float a0, a1, b0, b1;
-    unpack2(dist2_pair(xx, yy, pack2(a.x, a.y), pack2(a.z, a.w)), a0, a1);
-    unpack2(dist2_pair(xx, yy, pack2(b.x, b.y), pack2(b.z, b.w)), b0, b1);
-    best = min3f(best, a0, a1);
-    best = min3f(best, b0, b1);
-    p += 32u;
-  } while (p != p_end);
+    do {
+      best = pairs_min(best, p, xx, yy);
+      p += 32u;
+    } while (p != p_end);
+  }
   return best;
+}
+__device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float x, float y) {
+  const u64 xy = pack2(x, y);
+  return scan_rest(scan_first(pairs_s, e, xy), pairs_s, e, xy);
 }
 
 // The same scan, also returning the FIRST index that attains the minimum (-1 when no point is closer than the cap):
@@ -370,6 +387,8 @@ cudaError_t launch_candidate_grid(const DeviceState &d, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------
 // K2 (pruned)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kScanChunk = 4;  // steps whose nearest-point scans are issued together (= one TMA stage of controls)
+
 // What one thread needs besides its sample index (all CTA-uniform)
 struct ThreadCtx {
   const SolveParams *sP;    // shared copy of the per-solve constants
@@ -398,6 +417,9 @@ struct Rollout {
   bool steer_off;
   int *tap_row;
   int tap_t;
+  // the states of the current chunk whose nearest-point scans are still to do: position and cell entry
+  u64 pend_xy[kScanChunk];
+  uint32_t pend_cell[kScanChunk];
 
   __device__ __forceinline__ Rollout(const ThreadCtx &cx)
       : sP(*cx.sP), kb(*cx.kb), gv(cx.gv), pairs_s(cx.pairs_s), nom_s(cx.nom_s) {
@@ -428,21 +450,16 @@ struct Rollout {
     for (int u = 0; u < U; ++u) dst[u] = clamp_ref(raw[u], kb.lo[u], kb.hi[u]);
     if (steer_off) dst[2] = 0.f;  // FB:517
   }
-  // min_j min(d2, 1e4) of the current state over its cell's candidate range (+ the argmin for the debug tap)
-  __device__ __forceinline__ float nearest_d2(float x, float y) {
-    if (!TAP) return scan_pairs(pairs_s, cell, x, y);
-    int arg;
-    const float d2 = scan_pairs_arg(pairs_s, cell, x, y, &arg);
-    if (tap_row) tap_row[tap_t] = arg;
-    ++tap_t;
-    return d2;
-  }
-  // One iteration: the Euler step with the controls `cur` comes first, so that the candidate-range load of the NEXT
-  // state is in flight while the current state's distances and cost terms are evaluated (cell = entry of the
-  // current state, loaded one iteration earlier).
-  __device__ __forceinline__ void advance(const float *cur, const float *nxt) {
-    float x0, y0;
-    unpack2(xy, x0, y0);
+  // One control step, dynamics first: the Euler step with the controls `cur`, the candidate-range load of the NEXT
+  // state, and the cost terms that do not need the nearest point.  The state the step starts from is parked in slot
+  // SLOT of the chunk; its nearest-point scan happens in scans() -- a step's scan does not feed the dynamics, so the
+  // scans of kScanChunk consecutive steps are independent of each other and of the Euler steps in between, and are
+  // issued back to back: their shared-memory loads and FP chains overlap instead of each waiting behind its own
+  // data-dependent loop.  (Per step in sequence, a lone warp spent 80 % of its cycles stalled: profiles/r02_ncu_latency.txt.)
+  template <int SLOT>
+  __device__ __forceinline__ void step(const float *cur, const float *nxt) {
+    pend_xy[SLOT] = xy;
+    pend_cell[SLOT] = cell;
     const float sr0 = att.sr, cr0 = att.cr, sp0 = att.sp, cp0 = att.cp;
     float sd = 0.f, cd = 1.f, ch, sh;
     if (MODEL != kDiffDrive) sincos_f32<SMALL>(cur[2], sd, cd);
@@ -450,9 +467,7 @@ struct Rollout {
     step_heading<MODEL>(att, sd, cd, ch, sh);
     xy = fma2(mul2(pack2(cur[0], cur[0]), pack2(ch, sh)), pack2(dt, dt), xy);
     step_attitude<MODEL, SMALL>(att, cur, dt);
-    const uint32_t cell_next = grid_cell(gv, xy);
-    acc.path += nearest_d2(x0, y0);
-    cell = cell_next;
+    cell = grid_cell(gv, xy);
     const float dv = cur[0] - v_ref;
     acc.vel = fmaf(dv, dv, acc.vel);
     if (MODEL == kFullBody) {
@@ -464,11 +479,40 @@ struct Rollout {
       if (cur[0] < 0.f) acc.back = fmaf(cur[0], cur[0], acc.back);
     }
   }
+  // min_j min(d2, 1e4) of the N parked states over their cells' candidate ranges, added to the path cost in step
+  // order (the accumulation order of the contract); the debug instantiation records the argmin of each.
+  template <int N>
+  __device__ __forceinline__ void scans() {
+    float best[N];
+    if (TAP) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float x, y;
+        unpack2(pend_xy[k], x, y);
+        int arg;
+        best[k] = scan_pairs_arg(pairs_s, pend_cell[k], x, y, &arg);
+        if (tap_row) tap_row[tap_t] = arg;
+        ++tap_t;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) best[k] = scan_first(pairs_s, pend_cell[k], pend_xy[k]);
+#pragma unroll
+      for (int k = 0; k < N; ++k) best[k] = scan_rest(best[k], pairs_s, pend_cell[k], pend_xy[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc.path += best[k];
+  }
+  // one step and its scan right away (the ragged end of the horizon)
+  __device__ __forceinline__ void advance(const float *cur, const float *nxt) {
+    step<0>(cur, nxt);
+    scans<1>();
+  }
   __device__ __forceinline__ float finish(const float *st) {
     if (MODEL != kFullBody) {  // state T-1: path term only (D1)
-      float x, y;
-      unpack2(xy, x, y);
-      acc.path += nearest_d2(x, y);
+      pend_xy[0] = xy;
+      pend_cell[0] = cell;
+      scans<1>();
     }
     float yaw0_err = 0.f;
     if (MODEL == kFullBody) {  // FB:408; window points 0 and 1 are the first pair {x0, x1, y0, y1}
@@ -488,6 +532,7 @@ struct Rollout {
 // arithmetic, predicates, commit / wait groups -- cost ~14 and was dropped).
 constexpr int kStageSteps = 4;
 constexpr int kStages = 3;
+static_assert(kStageSteps == kScanChunk, "the rollout loop parks one TMA stage of steps per scan chunk");
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -570,11 +615,11 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
   for (int tile = 0; t + kStageSteps <= n_iter; t += kStageSteps, ++tile) {
     const unsigned base = col + slot * kTileBytes;
     r.make(t + 1, base + kStepBytes, 128u, cb);
-    r.advance(ca, cb);
+    r.template step<0>(ca, cb);
     r.make(t + 2, base + 2 * kStepBytes, 128u, ca);
-    r.advance(cb, ca);
+    r.template step<1>(cb, ca);
     r.make(t + 3, base + 3 * kStepBytes, 128u, cb);
-    r.advance(ca, cb);
+    r.template step<2>(ca, cb);
     const unsigned done = slot;
     if (++slot == kStages) {
       slot = 0;
@@ -582,7 +627,8 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
     }
     mbar_wait(tc.bar_s + slot * 8u, parity);
     r.make(t + 4, col + slot * kTileBytes, 128u, ca);
-    r.advance(cb, ca);
+    r.template step<3>(cb, ca);
+    r.template scans<kScanChunk>();
     // Refill the finished slot with the tile kStages ahead.  Every value the lanes loaded from it has been consumed
     // by an Euler step above (cb, its last row, by the advance just before this line), so no shared-memory read of
     // the slot is outstanding when the bulk copy is issued; __syncwarp() orders the lanes.
@@ -689,11 +735,12 @@ size_t pruned_tma_smem_bytes(int T, int planes, int U) {
          sizeof(float) * ((size_t)planes + 2 * U);
 }
 
-// resident CTAs per SM the register allocation must allow: 9 (56 registers) for the two- and three-control models --
-// what the rollout loop needs anyway; the bound only keeps the rare-path code of the scan from raising it -- and 5
-// for the full-body model
+// resident CTAs per SM the register allocation must allow: 8 (64 registers, no spills) for the two- and
+// three-control models, 5 for the full-body model.  Measured with the chunked scans (K = 2^20 / 2^17 / 4096):
+// 9 CTAs (56 registers, 12 bytes spilled) 0.519 / 0.098 / 0.0279 ms, 8 CTAs 0.518 / 0.095 / 0.0272, 7 CTAs
+// (72 registers) 0.523 / 0.094 / 0.0272
 #ifndef MPPI_K2_MINBLOCKS
-#define MPPI_K2_MINBLOCKS 9
+#define MPPI_K2_MINBLOCKS 8
 #endif
 #ifndef MPPI_K2_MINBLOCKS_FB
 #define MPPI_K2_MINBLOCKS_FB 5
@@ -909,12 +956,17 @@ __global__ void __launch_bounds__(256)
     return;
   }
   if (MODE == 1) {
-    if (R > 1 && !last_block_of_grid(ticket, (unsigned)R)) return;
-    if (R == 1) {
+    if (R > 1) {
+      if (!last_block_of_grid(ticket, (unsigned)R)) return;
+      exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R);
+    } else if (in_regs) {  // one robot: this block holds the whole record in registers -- push it from there
+      exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R, true,
+                         threadIdx.x < ncol ? mine0 : 0.f, (int)(threadIdx.x + blockDim.x) < ncol ? mine1 : 0.f);
+    } else {
       __threadfence();
       __syncthreads();
+      exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R);
     }
-    exchange_and_merge(hdr, record, x, u_new, nominal, stats, counter, planes, part_stride, R);
   }
 }
 
