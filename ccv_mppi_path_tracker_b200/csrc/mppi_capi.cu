@@ -83,6 +83,7 @@ struct mppi_handle_s {
   bool host_windows_staged = true; // the staged block carries host-built windows (must be copied)
   int opt_upload_warm_start = 1;   // mppi_solve copies the caller's u_nominal to the device (0: keeps the device's own)
   float *h_out = nullptr, *d_out = nullptr;
+  bool out_mapped = false;  // small results: the tail kernel writes them straight into the pinned host block
   size_t out_bytes = 0;
   // host-side per-robot inputs
   std::vector<std::vector<double>> path;
@@ -457,7 +458,7 @@ int capture(mppi_handle h, bool with_copies, cudaGraphExec_t *out) {
   int rc = MPPI_OK;
   if (with_copies) rc = enqueue_h2d(h, h->opt_upload_warm_start != 0, h->stream);
   if (rc == MPPI_OK) rc = issue_kernels(h, h->stream, true);
-  if (rc == MPPI_OK && with_copies) {
+  if (rc == MPPI_OK && with_copies && !h->out_mapped) {
     cudaError_t e = cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream);
     if (e != cudaSuccess) rc = fail(h, MPPI_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -595,8 +596,16 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   memset(h->h_out, 0, h->out_bytes);
   CU_NEW(cudaMalloc((void **)&h->d_in, h->in_bytes));
   CU_NEW(cudaMemset(h->d_in, 0, h->in_bytes));
-  CU_NEW(cudaMalloc((void **)&h->d_out, h->out_bytes));
-  CU_NEW(cudaMemset(h->d_out, 0, h->out_bytes));
+  // Results of up to 16 KB (single robots: (T-1) x U controls + 4 statistics) need no device copy and no D2H node:
+  // the pinned block is addressable from the device (unified addressing), the tail kernel stores into it over PCIe
+  // and the host reads it after the stream synchronisation it does anyway.  Fleets keep the device buffer + one copy.
+  h->out_mapped = h->out_bytes <= 16 * 1024;
+  if (h->out_mapped) {
+    h->d_out = h->h_out;
+  } else {
+    CU_NEW(cudaMalloc((void **)&h->d_out, h->out_bytes));
+    CU_NEW(cudaMemset(h->d_out, 0, h->out_bytes));
+  }
   d.hdr = reinterpret_cast<SolveHeader *>(h->d_in);
   d.window = reinterpret_cast<float *>(h->d_in + h->window_off);
   d.state = reinterpret_cast<float *>(h->d_in + h->state_off);
@@ -678,7 +687,8 @@ int mppi_destroy(mppi_handle h) {
   cudaFree(d.nearest);
   cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg);
   cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
-  cudaFree(h->d_in); cudaFree(h->d_out);
+  cudaFree(h->d_in);
+  if (!h->out_mapped) cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->staged) cudaEventDestroy(h->staged);
@@ -950,7 +960,7 @@ int mppi_download(mppi_handle h, double *u_nominal) {
   if (!h) return MPPI_ERR_INVALID;
   if (!u_nominal) return fail(h, MPPI_ERR_INVALID, "u_nominal is NULL");
   CU_TRY(h, cudaSetDevice(h->device));
-  CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (!h->out_mapped) CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->staged_pending = false;
   return copy_out(h, u_nominal);
@@ -959,7 +969,7 @@ int mppi_download(mppi_handle h, double *u_nominal) {
 int mppi_synchronize(mppi_handle h) {
   if (!h) return MPPI_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
-  if (h->p2p) {  // bring the statistics over: a peer-exchange time-out of an enqueued solve is reported here too
+  if (h->p2p && !h->out_mapped) {  // bring the statistics over: a peer-exchange time-out of an enqueued solve is reported here too
     const size_t off = sizeof(float) * (size_t)h->R * h->d.planes;
     CU_TRY(h, cudaMemcpyAsync((char *)h->h_out + off, (char *)h->d_out + off, h->out_bytes - off, cudaMemcpyDeviceToHost,
                               h->stream));
@@ -1104,7 +1114,7 @@ int mppi_get_stats(mppi_handle h, int robot, double *stats) {
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   float s[4];
-  CU_TRY(h, cudaMemcpy(s, h->d.stats + (size_t)robot * 4, sizeof s, cudaMemcpyDeviceToHost));
+  CU_TRY(h, cudaMemcpy(s, h->d.stats + (size_t)robot * 4, sizeof s, cudaMemcpyDefault));  // device or mapped host
   stats[0] = s[0];
   stats[1] = s[1];
   stats[2] = s[2];
