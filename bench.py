@@ -757,7 +757,7 @@ def main():
 
 def sweep_k(device, model="diff_drive", T=100, n_solves=60):
     """BASELINE.json's metric is quoted "vs K": rollout-steps/s (device-resident, back-to-back enqueues, CUDA events)
-    and host-observed solve latency p50 (mppi_solve() with host buffers, CUDA graph) for K = 2^10 .. 2^20, one robot,
+    and host-observed solve latency p50 (mppi_solve() with host buffers; CUDA graph up to K = 2^15) for K = 2^10 .. 2^20, one robot,
     launch-file parameters, stationary steps as in the bench line.  One GPU."""
     import torch
     from ccv_mppi_path_tracker_b200 import CONTROLLERS, _capi
@@ -788,7 +788,7 @@ def sweep_k(device, model="diff_drive", T=100, n_solves=60):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n_solves
         ctl.set_option(_capi.OPT_FEEDBACK_WARM_START, 1)
-        ctl.use_graph(True)
+        ctl.use_graph(K * (T - 1) <= (1 << 22))  # graph replay where launch overhead matters, as in the bench line
         for _ in range(5):
             plant_step(model, states, ctl.solve(states, 0.1).reshape(1, T - 1, U), 0.1)
         ts = np.empty(n_solves)
