@@ -60,6 +60,30 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(res["p2p_fused"], res["nccl_fused"])
     rng_ = np.array(case["sp"]["u_max"][:3]) - np.array(case["sp"]["u_min"][:3])
     assert (np.abs(res["p2p"] - res["p2p_fused"]) / rng_).max() < 5e-4  # per-CTA vs per-chunk summation order
+    # a peer that stops solving: the other rank's solve fails after MPPI_OPT_EXCHANGE_TIMEOUT_MS instead of merging
+    # garbage, and its controls / warm start keep their previous values
+    ctl = CONTROLLERS["steering"](launch=True, device=rank, horizon=T, num_samples=K // world)
+    ctl.set_path(case["path"])
+    ctl.set_seed(77, 0)
+    ctl.set_shard(rank * (K // world), K, 0)
+    ctl.set_option(_capi.OPT_EXCHANGE_TIMEOUT_MS, 50)
+    t = torch.frombuffer(bytearray(ctl.comm_export(world)), dtype=torch.uint8).cuda()
+    allh = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    ctl.comm_connect(b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh), rank, world)
+    dist.barrier()
+    u_ok = ctl.solve(case["state"], case["dt"]).copy()
+    dist.barrier()
+    if rank == 0:
+        try:
+            ctl.solve(case["state"], case["dt"])
+            timed_out = False
+        except _capi.MppiError as e:
+            timed_out = e.code == _capi.MPPI_ERR_NCCL and "timed out" in str(e)
+        assert timed_out, "rank 0 solved alone and did not report the missing peer"
+        assert np.array_equal(ctl.optimal_solution[0], u_ok)  # controls untouched by the failed solve
+    dist.barrier()
+    ctl.close()
     np.save(os.path.join(out_dir, f"u_{rank}.npy"), res["p2p"])
     dist.barrier()
     dist.destroy_process_group()

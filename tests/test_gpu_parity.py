@@ -396,7 +396,10 @@ def test_large_angles_take_the_general_instantiation(model, overrides, dt):
 
 
 @pytest.mark.parametrize("model,K,T,R", [("diff_drive", 1024, 50, 3), ("diff_drive", 4099, 101, 1), ("steering", 333, 50, 2),
-                                         ("full_body", 1030, 27, 1), ("full_body", 2048, 100, 1)])
+                                         ("full_body", 1030, 27, 1), ("full_body", 2048, 100, 1),
+                                         ("diff_drive", 9000, 30, 2),    # several record groups per robot AND several robots
+                                         ("full_body", 700, 120, 1),     # 599 record columns: more than two per tail thread
+                                         ("diff_drive", 140000, 24, 1)])  # 1094 CTA records: 35 groups
 def test_fused_weighted_controls_match_the_separate_kernels(model, K, T, R):
     """Many-robot handles and mid-sized single solves reduce the weighted controls inside K2 (per-CTA records against
     the CTA's own minimum, then a log-sum-exp rescale + finalize + merge in one tail kernel) instead of K3 + K4 + K5 +
