@@ -116,8 +116,8 @@ struct mppi_handle_s {
   int robot_offset = 0;
   // K0 (candidate grid) runs beside K1 (noise): they are independent
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_grid = nullptr, ev_join = nullptr, ev_k2done = nullptr, ev_epsfree = nullptr;
-  bool staged_recorded = false, k2_recorded = false;  // the events have been recorded on the current stream at least once
+  cudaEvent_t ev_fork = nullptr, ev_grid = nullptr, ev_join = nullptr, ev_readers = nullptr;
+  bool staged_recorded = false, readers_recorded = false;  // the events have been recorded on the current stream at least once
   // graphs
   bool use_graph = false;
   cudaGraphExec_t exec_kernels = nullptr, exec_solve = nullptr;
@@ -254,42 +254,47 @@ bool fused_tail_for(mppi_handle h, const DeviceState &t) {
 }
 
 // the kernel sequence of one solve on stream s (also what gets captured into the graph)
-//   main:  . . . . . . . . . . . . . . K2 -> (K3 -> K4 | -) -> tail (finalize / exchange / merge; counter++)
-//   side:  [K-1 window] -> K0 candidate grid -> K1 noise of the NEXT solve (prefetch)
-// K2 waits for K0; the tail waits for K1 (the generator reads the solve counter that the tail advances).
-// Plain stream launches (capturing = false) let the side stream start as soon as ITS inputs are there -- the staged
-// pose / window of this solve and the end of the previous solve's K2 (which reads the window and the grid) -- so the
-// window builder, the candidate grid and the generator run under the previous solve's K3 / K4 / tail.  Inside a
-// graph the side stream forks from the first node.
+//   plain stream launches (back-to-back throughput):
+//     main:  . . . . . . . . . . . . . . K2 -> (K3 -> K4 | -) -> tail (finalize / exchange / merge; counter++)
+//     side:  [K-1 window] -> K0 candidate grid -> K1 noise of the NEXT solve (prefetch)
+//     The side stream starts as soon as ITS inputs are there -- the staged pose / window of this solve and the end of
+//     the previous solve's last reader of window, grid and noise buffer -- so window builder, candidate grid and
+//     generator run under the previous solve's K4 / tail.  K2 waits for K0.
+//   inside a CUDA graph (the synchronous latency path; nothing of another solve to overlap with):
+//     main:  [K-1] -> K0 -> K2 -> (K3 -> K4 | -) -> tail          side:  K1 noise of the next solve
+//     K2, K3, K4 are programmatic dependents of the kernel in front of them: their launch latency and K2's input
+//     prologue overlap the predecessor (pdl_wait() in the kernels).
+// The tail waits for K1: the generator reads the solve counter that the tail advances.
 int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   const DeviceState &d = h->d;
+  DeviceState dp = d;  // launch descriptor for the kernels that may start under their predecessor
+  dp.pdl = true;
   int n = 0;
   bool want_nearest, want_states;
   const int scan = effective_scan(h, &want_nearest, &want_states);
   const bool prefetch = prefetch_on(h, scan);
   const bool dev_win = device_windows(h);
-  const bool side = scan == MPPI_SCAN_PRUNED;
-  cudaStream_t ws = side ? h->side_stream : s;  // where the window builder runs
+  const bool pruned = scan == MPPI_SCAN_PRUNED;
+  const bool side = pruned && (!capturing || prefetch);  // something runs on the side stream
+  cudaStream_t gs = (pruned && !capturing) ? h->side_stream : s;  // where window builder and candidate grid run
   if (side) {
     if (capturing) {
       CU_TRY(h, cudaEventRecord(h->ev_fork, s));
       CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     } else {
       if (h->staged_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->staged, 0));
-      if (h->k2_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_k2done, 0));
+      if (h->readers_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_readers, 0));
     }
   }
   if (dev_win) {
-    CU_TRY(h, launch_window_builder(d, ws));
+    CU_TRY(h, launch_window_builder(d, gs));
     ++n;
   }
-  if (side) {
-    CU_TRY(h, launch_candidate_grid(d, h->side_stream));
-    CU_TRY(h, cudaEventRecord(h->ev_grid, h->side_stream));
+  if (pruned) {
+    CU_TRY(h, launch_candidate_grid(d, gs));
     ++n;
+    if (!capturing) CU_TRY(h, cudaEventRecord(h->ev_grid, h->side_stream));
     if (prefetch) {
-      // the buffer of solve n+1 is the buffer of solve n-1: its last reader (K4, or the fused K2) must be done
-      if (!capturing && h->k2_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_epsfree, 0));
       CU_TRY(h, launch_noise(d, 1, h->side_stream));
       CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
       ++n;
@@ -299,25 +304,26 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
     CU_TRY(h, launch_noise(d, 0, s));
     ++n;
   }
-  if (side) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_grid, 0));
+  if (pruned && !capturing) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_grid, 0));
   const bool fused = fused_controls(h, scan);
-  CU_TRY(h, launch_rollout_cost(d, scan, want_nearest, want_states, fused, s));
+  // K2 directly behind K0 on the same stream (graph, no generator in between): a programmatic dependent
+  const bool k2_pdl = pruned && capturing && (h->external_noise || prefetch);
+  CU_TRY(h, launch_rollout_cost(k2_pdl ? dp : d, scan, want_nearest, want_states, fused, s));
   ++n;
-  if (!capturing) {
-    CU_TRY(h, cudaEventRecord(h->ev_k2done, s));
-    h->k2_recorded = true;
-  }
   h->last_fused = fused;
   h->weights_valid = !fused;  // the per-sample weights are a debug tap on the fused path (mppi_get_weights)
   if (!fused) {
     if (!fused_weights(h)) {
-      CU_TRY(h, launch_weights(d, false, s));
+      CU_TRY(h, launch_weights(dp, false, s));
       ++n;
     }
-    CU_TRY(h, launch_weighted_controls(d, fused_weights(h), s));
+    CU_TRY(h, launch_weighted_controls(dp, fused_weights(h), s));
     ++n;
   }
-  if (!capturing) CU_TRY(h, cudaEventRecord(h->ev_epsfree, s));  // the last reader of this solve's normals is queued
+  if (!capturing) {  // the last reader of this solve's window, grid and normals is queued
+    CU_TRY(h, cudaEventRecord(h->ev_readers, s));
+    h->readers_recorded = true;
+  }
   if (prefetch) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));  // join before the counter advances
   h->launch_count = n;
   if (fused) {  // rescale + finalize + merge (+ exchange) in one launch
@@ -574,8 +580,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_grid, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  CU_NEW(cudaEventCreateWithFlags(&h->ev_k2done, cudaEventDisableTiming));
-  CU_NEW(cudaEventCreateWithFlags(&h->ev_epsfree, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_readers, cudaEventDisableTiming));
   CU_NEW(cudaDeviceGetAttribute(&h->sm_clock_khz, cudaDevAttrClockRate, device));
   if (h->sm_clock_khz <= 0) h->sm_clock_khz = 1965000;
   d.xchg_timeout_cycles = (long long)(h->opt_timeout_ms * (double)h->sm_clock_khz);
@@ -695,8 +700,7 @@ int mppi_destroy(mppi_handle h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_grid) cudaEventDestroy(h->ev_grid);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->ev_k2done) cudaEventDestroy(h->ev_k2done);
-  if (h->ev_epsfree) cudaEventDestroy(h->ev_epsfree);
+  if (h->ev_readers) cudaEventDestroy(h->ev_readers);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

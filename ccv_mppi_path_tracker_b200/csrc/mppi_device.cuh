@@ -5,6 +5,13 @@
 
 namespace mppi {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialisation attribute may start
+// while its predecessor in the stream still runs; pdl_wait() returns once that predecessor has completed and its
+// writes are visible (a no-op for an ordinary launch), pdl_trigger() lets the successor of THIS kernel start early.
+// Used along the chain K0 -> K2 -> K3 -> K4: the successor's launch latency and input prologue overlap the predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

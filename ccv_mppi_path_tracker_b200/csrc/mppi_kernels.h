@@ -98,6 +98,7 @@ struct DeviceState {
   float *cta_part = nullptr;  // [R][ceil(K/128)][rec_stride] per-CTA records {m, S, Q, -, N[P]} of the fused K2
   int k4_groups = 0;  // > 0: plane groups per K4 block (tuning); else by the number of blocks
   unsigned int *tail_ticket = nullptr;  // [R + 1] "last block" tickets of the one-kernel tail (fused-controls path)
+  bool pdl = false;           // launch K2 / K3 / K4 as programmatic dependents of the kernel in front of them
   int side_carveout = -1;     // shared-memory carve-out (per cent) given to the side-stream kernels: K2's own
   ControlBounds bounds = {};  // kernel parameter of K2 (kept equal to hdr->P.u_min / u_max by the host)
   bool eps_map_valid = false;
@@ -111,6 +112,23 @@ struct DeviceState {
 cudaError_t set_carveout(const void *kernel, int percent);
 // the split the driver picks for the K2 instantiation of this handle (mppi_rollout_pruned.cu)
 int rollout_carveout_percent(const DeviceState &d);
+
+// kernel launch with or without the programmatic-dependent-launch attribute (see pdl_wait() in mppi_device.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                 Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kHeaderBytes = 256;
 constexpr int kStateStride = 4;     // floats per robot of the state record {yaw, roll, pitch, -} (x = y = 0: robot frame)

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(128)
   constexpr int kCellsPerBlock = 128 / LANES;
   extern __shared__ __align__(16) float2 s_win[];
   __shared__ GridHeader s_h;
+  pdl_trigger();  // K2 may start its prologue (inputs -> shared memory) now; it waits for this grid before the lookup
   const int robot = blockIdx.y;
   float margin = margin_abs;
   if (!(margin > 0.f)) margin = fminf(fmaxf(0.25f * fabsf(hdr->P.v_ref) * hdr->P.dt * (float)(T - 1), 0.5f), 6.0f);
@@ -769,8 +770,9 @@ __global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB
   float *s_nom = reinterpret_cast<float *>(s_pairs + NP + 1);
 
   const float *g_win = window + (size_t)robot * win_stride;
+  pdl_trigger();  // the reduction kernel behind may be launched; it waits for this grid before it reads a cost
+  // inputs of the solve (header, window, warm start): ready before the candidate grid in front of this kernel started
   load_params_to_shared(&sP, hdr);
-  if (threadIdx.x == 0) s_gh = ghdr[robot];
   if (threadIdx.x < 4 * kStages) mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[threadIdx.x]), 1u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int q = threadIdx.x; q < NP + 1; q += blockDim.x) {
@@ -780,6 +782,8 @@ __global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB
   }
   for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
     s_nom[j] = j < planes ? nominal[(size_t)robot * planes + j] : 0.f;
+  pdl_wait();  // the candidate grid (K0) is complete and visible from here on
+  if (threadIdx.x == 0) s_gh = ghdr[robot];
   __syncthreads();
 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1039,10 +1043,12 @@ cudaError_t launch_rollout_cost_pruned(const DeviceState &d, bool fused, bool wr
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
     }                                                                                                            \
-    rollout_cost_tma_kernel<M, TAP><<<grid, 128, smem, s>>>(                                                     \
-        d.eps_map, d.bounds, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, d.grid_cells, d.cost, d.cmin, d.K, \
-        d.planes, d.win_stride, d.T, d.grid_max_cells, d.eps, d.Kp, fused ? d.cta_part : nullptr, d.rec_stride,  \
-        d.counter, (uint32_t)(d.eps_buffers - 1), d.eps_buf_elems, nearest);                                     \
+    cudaError_t le = launch_kernel(d.pdl, rollout_cost_tma_kernel<M, TAP>, grid, dim3(128), smem, s, d.eps_map,  \
+                                   d.bounds, d.hdr, d.nominal, d.window, d.state, d.grid_hdr, d.grid_cells, d.cost, \
+                                   d.cmin, d.K, d.planes, d.win_stride, d.T, d.grid_max_cells, d.eps, d.Kp,      \
+                                   fused ? d.cta_part : nullptr, d.rec_stride, d.counter,                        \
+                                   (uint32_t)(d.eps_buffers - 1), d.eps_buf_elems, nearest);                     \
+    if (le != cudaSuccess) return le;                                                                            \
   } while (0)
 #define MPPI_LAUNCH_TMA_MODEL(TAP)                                                                               \
   switch (d.model) {                                                                                             \
