@@ -1266,7 +1266,8 @@ int mppi_comm_export(mppi_handle h, int n_ranks, void *handle_out) {
   if (h->comm || h->xchg_buf) return fail(h, MPPI_ERR_STATE, "communicator already initialised");
   CU_TRY(h, cudaSetDevice(h->device));
   const DeviceState &d = h->d;
-  const size_t bytes = kExchangeHeaderBytes + sizeof(float) * 2 * (size_t)n_ranks * d.R * d.rec_stride;
+  // slots[2 parities][n_ranks][R][rec_stride] of 8-byte words {payload, stamp} (mppi_device.cuh)
+  const size_t bytes = kExchangeHeaderBytes + sizeof(unsigned long long) * 2 * (size_t)n_ranks * d.R * d.rec_stride;
   CU_TRY(h, cudaMalloc(&h->xchg_buf, bytes));
   CU_TRY(h, cudaMemset(h->xchg_buf, 0, bytes));
   CU_TRY(h, cudaMalloc((void **)&h->d.xchg_seq, sizeof(unsigned int)));

@@ -66,81 +66,167 @@ __device__ __forceinline__ bool last_block_of_grid(unsigned int *ticket, unsigne
   return s_last;
 }
 
-// Exchange buffer of one rank: flags[2][G] then slots[2][G][R][rec]; parity = solve sequence & 1.  A rank can run at
-// most one solve ahead of a peer (its next merge needs that peer's next record, which the peer pushes only after its
-// own merge of the current solve), so two parities are enough.
-__device__ __forceinline__ unsigned int *xchg_flags(void *base, int parity, int G) {
-  return reinterpret_cast<unsigned int *>(base) + parity * G;
+// Exchange buffer of one rank: slots[2][G][R][rec] of 8-byte words {payload (float bits), stamp}; parity = solve
+// sequence & 1, stamp = sequence + 1.  Data and "it has arrived" travel in ONE aligned 8-byte store (the protocol NCCL
+// calls LL): no fence, no separate flag, no second trip -- the receiver polls the words it needs and has the payload
+// in its registers the moment the stamp matches.  A rank can run at most one solve ahead of a peer (its next merge
+// needs that peer's next record, which the peer pushes only after its own merge of the current solve), so two
+// parities are enough and a stamp can never be mistaken for another solve's.
+__device__ __forceinline__ unsigned long long *xchg_slot(void *base, int parity, int g, int G, size_t slot_elems) {
+  return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + kExchangeHeaderBytes) +
+         ((size_t)parity * G + g) * slot_elems;
 }
-__device__ __forceinline__ float *xchg_slot(void *base, int parity, int g, int G, size_t slot_floats) {
-  return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + kExchangeHeaderBytes) +
-         ((size_t)parity * G + g) * slot_floats;
+__device__ __forceinline__ unsigned long long xchg_pack(float v, unsigned int stamp) {
+  return ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(v);
+}
+// spins until the word carries `stamp`; returns false on time-out
+__device__ __forceinline__ bool xchg_poll(const unsigned long long *word, unsigned int stamp, long long t0,
+                                          long long timeout_cycles, float &payload) {
+  const volatile unsigned long long *w = word;
+  for (;;) {
+    const unsigned long long v = *w;
+    if ((unsigned int)(v >> 32) == stamp) {
+      payload = __uint_as_float((unsigned int)v);
+      return true;
+    }
+    if (clock64() - t0 > timeout_cycles) return false;
+  }
 }
 
-// The exchange step of a sample-sharded solve, run by ONE block once this rank's records [R][rec_stride] are complete:
-// stores them into every rank's exchange buffer (NVLink P2P stores; own buffer included), raises the flags, waits for
-// the peers' flags, then merges all ranks' records in rank order (log-sum-exp merge, bit-identical on every rank):
-// u_new, warm start, stats, counter++.  A peer that does not arrive within timeout_cycles leaves controls and warm
-// start untouched and sets stats[3] = 1 (the host then reports MPPI_ERR_NCCL).
+constexpr int kExchangeRegRanks = 8;  // ranks whose records the merging block keeps in registers (one robot)
+
+// The exchange step of a sample-sharded solve, run by ONE block once this rank's records [R][rec_stride] are complete
+// (in `record`, or -- one robot, at most two elements per thread -- still in the caller's registers): stores them into
+// every rank's exchange buffer (NVLink P2P stores; own buffer included), polls the peers' words, then merges all ranks'
+// records in rank order (log-sum-exp merge, bit-identical on every rank and to merge_kernel): u_new, warm start, stats,
+// counter++.  A peer that does not arrive within timeout_cycles leaves controls and warm start untouched and sets
+// stats[3] = 1 (the host then reports MPPI_ERR_NCCL).
 __device__ __forceinline__ void exchange_and_merge(const SolveHeader *__restrict__ hdr, const float *record,
                                                    const ExchangeArgs &x, float *__restrict__ u_new,
                                                    float *__restrict__ nominal, float *__restrict__ stats,
                                                    uint32_t *__restrict__ counter, int planes, int rec_stride, int R,
                                                    bool own_in_regs = false, float own0 = 0.f, float own1 = 0.f) {
   __shared__ int s_timeout;
+  __shared__ float s_head[3][kExchangeRegRanks];  // {m_g, S_g, Q_g} of every rank (register path)
   const int G = x.G;
   const unsigned int n = *x.seq;
+  const unsigned int stamp = n + 1u;
   const int parity = (int)(n & 1u);
-  const size_t slot_floats = (size_t)R * rec_stride;
+  const size_t slot_elems = (size_t)R * rec_stride;
+  const float inv_lambda = hdr->inv_lambda;
+  const long long t0 = clock64();
   if (threadIdx.x == 0) s_timeout = 0;
-  // every element is read once (or is still in the caller's registers: own_in_regs, one robot, <= 2 elements per
-  // thread) and stored to all G buffers: the stores are posted, nothing below depends on them before the fence
-  int slot = 0;
-  for (size_t k = threadIdx.x; k < slot_floats; k += blockDim.x, ++slot) {
-    const float v = own_in_regs ? (slot == 0 ? own0 : own1) : __ldcg(record + k);
-    for (int g = 0; g < G; ++g) xchg_slot(x.peers[g], parity, x.rank, G, slot_floats)[k] = v;
-  }
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < G) {
-    volatile unsigned int *f = xchg_flags(x.peers[threadIdx.x], parity, G) + x.rank;
-    *f = n + 1u;
-    // flags of one parity only grow (n+1, n+3, ...): a later value can never be mistaken for this solve's
-    volatile unsigned int *mine = xchg_flags(x.xbuf, parity, G) + threadIdx.x;
-    const long long t0 = clock64();
-    while (*mine != n + 1u) {
-      if (clock64() - t0 > x.timeout_cycles) {
-        s_timeout = 1;
-        break;
+  const bool reg_path = R == 1 && G <= kExchangeRegRanks && slot_elems <= 2 * (size_t)blockDim.x;
+  if (reg_path) {
+    // ---- one robot: every thread owns (up to) two record elements of every rank, start to finish ----------------
+    const size_t k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
+    const bool has0 = k0 < slot_elems, has1 = k1 < slot_elems;
+    const float v0 = own_in_regs ? own0 : (has0 ? __ldcg(record + k0) : 0.f);
+    const float v1 = own_in_regs ? own1 : (has1 ? __ldcg(record + k1) : 0.f);
+    for (int g = 0; g < G; ++g) {  // posted stores, all peers
+      unsigned long long *dst = xchg_slot(x.peers[g], parity, x.rank, G, slot_elems);
+      if (has0) *reinterpret_cast<volatile unsigned long long *>(dst + k0) = xchg_pack(v0, stamp);
+      if (has1) *reinterpret_cast<volatile unsigned long long *>(dst + k1) = xchg_pack(v1, stamp);
+    }
+    float a0[kExchangeRegRanks], a1[kExchangeRegRanks];
+    bool ok = true;
+#pragma unroll
+    for (int g = 0; g < kExchangeRegRanks; ++g) {
+      a0[g] = a1[g] = 0.f;
+      if (g < G) {
+        const unsigned long long *src = xchg_slot(x.xbuf, parity, g, G, slot_elems);
+        if (has0) ok = xchg_poll(src + k0, stamp, t0, x.timeout_cycles, a0[g]) && ok;
+        if (has1) ok = xchg_poll(src + k1, stamp, t0, x.timeout_cycles, a1[g]) && ok;
       }
     }
+    if (!ok) s_timeout = 1;
+    if (threadIdx.x < 3) {
+#pragma unroll
+      for (int g = 0; g < kExchangeRegRanks; ++g) s_head[threadIdx.x][g] = a0[g];
+    }
+    __syncthreads();
+    const bool timed_out = s_timeout != 0;
+    float m = s_head[0][0];
+    for (int g = 1; g < G; ++g) {
+      const float mg = s_head[0][g];
+      m = mg < m ? mg : m;
+    }
+    float S = 0.f, Q = 0.f, scale[kExchangeRegRanks];
+#pragma unroll
+    for (int g = 0; g < kExchangeRegRanks; ++g) {
+      scale[g] = 0.f;
+      if (g < G) {
+        scale[g] = merge_scale(s_head[0][g], m, inv_lambda, G);
+        S = fmaf(scale[g], s_head[1][g], S);
+        Q = fmaf(scale[g] * scale[g], s_head[2][g], Q);
+      }
+    }
+    if (!timed_out) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col = (int)(half ? k1 : k0);
+        if (col >= 4 && col < 4 + planes) {
+          float N = 0.f;
+#pragma unroll
+          for (int g = 0; g < kExchangeRegRanks; ++g)
+            if (g < G) N = fmaf(scale[g], half ? a1[g] : a0[g], N);
+          const float u = N / S;
+          u_new[col - 4] = u;
+          if (nominal) nominal[col - 4] = u;
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      stats[0] = m;
+      stats[1] = S;
+      stats[2] = S * S / Q;
+      stats[3] = timed_out ? 1.f : 0.f;  // != 0: a peer's record did not arrive in time
+      *counter = *counter + 1u;
+      *x.seq = n + 1u;
+    }
+    return;
   }
-  __threadfence_system();
+  // ---- general case (several robots, many ranks): push, poll every word, merge from the buffer ---------------------
+  {
+    int slot = 0;
+    for (size_t k = threadIdx.x; k < slot_elems; k += blockDim.x, ++slot) {
+      const float v = own_in_regs ? (slot == 0 ? own0 : own1) : __ldcg(record + k);
+      for (int g = 0; g < G; ++g)
+        *reinterpret_cast<volatile unsigned long long *>(xchg_slot(x.peers[g], parity, x.rank, G, slot_elems) + k) =
+            xchg_pack(v, stamp);
+    }
+    bool ok = true;
+    for (size_t k = threadIdx.x; k < slot_elems; k += blockDim.x)
+      for (int g = 0; g < G; ++g) {
+        float unused;
+        ok = xchg_poll(xchg_slot(x.xbuf, parity, g, G, slot_elems) + k, stamp, t0, x.timeout_cycles, unused) && ok;
+      }
+    if (!ok) s_timeout = 1;
+  }
   __syncthreads();
   const bool timed_out = s_timeout != 0;
-  const float inv_lambda = hdr->inv_lambda;
+  auto payload = [&](int g, size_t k) {  // arrived (polled above): a plain L2 read of the word's low half
+    return __uint_as_float((unsigned int)__ldcg(xchg_slot(x.xbuf, parity, g, G, slot_elems) + k));
+  };
   for (int robot = 0; robot < R; ++robot) {
-    // the records were written by peers into this GPU's memory: read them through L2 (__ldcg), never L1
-    const float *recs = xchg_slot(x.xbuf, parity, 0, G, slot_floats) + (size_t)robot * rec_stride;
-    float m = __ldcg(recs);
+    const size_t base = (size_t)robot * rec_stride;
+    float m = payload(0, base);
     for (int g = 1; g < G; ++g) {
-      const float mg = __ldcg(recs + (size_t)g * slot_floats);
+      const float mg = payload(g, base);
       m = mg < m ? mg : m;
     }
     float S = 0.f, Q = 0.f;
     for (int g = 0; g < G; ++g) {
-      const float *r = recs + (size_t)g * slot_floats;
-      const float a = merge_scale(__ldcg(r), m, inv_lambda, G);
-      S = fmaf(a, __ldcg(r + 1), S);
-      Q = fmaf(a * a, __ldcg(r + 2), Q);
+      const float a = merge_scale(payload(g, base), m, inv_lambda, G);
+      S = fmaf(a, payload(g, base + 1), S);
+      Q = fmaf(a * a, payload(g, base + 2), Q);
     }
     if (!timed_out) {
       for (int p = threadIdx.x; p < planes; p += blockDim.x) {
         float N = 0.f;
-        for (int g = 0; g < G; ++g) {
-          const float *r = recs + (size_t)g * slot_floats;
-          N = fmaf(merge_scale(__ldcg(r), m, inv_lambda, G), __ldcg(r + 4 + p), N);
-        }
+        for (int g = 0; g < G; ++g)
+          N = fmaf(merge_scale(payload(g, base), m, inv_lambda, G), payload(g, base + 4 + p), N);
         const float u = N / S;
         u_new[(size_t)robot * planes + p] = u;
         if (nominal) nominal[(size_t)robot * planes + p] = u;

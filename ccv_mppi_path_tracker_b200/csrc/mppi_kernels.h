@@ -132,7 +132,7 @@ inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, 
 
 constexpr int kHeaderBytes = 256;
 constexpr int kStateStride = 4;     // floats per robot of the state record {yaw, roll, pitch, -} (x = y = 0: robot frame)
-constexpr int kExchangeHeaderBytes = 256;  // flags[2][G] (G <= 32) at the start of an exchange buffer
+constexpr int kExchangeHeaderBytes = 256;  // reserved head of an exchange buffer (keeps the slots 256-byte aligned)
 constexpr int kWeightBlock = 256;   // threads of the weight kernel, 4 samples per thread
 constexpr int kReduceBlock = 256;   // threads of the weighted-control reduction
 constexpr int kReduceChunk = 4096;  // samples per (plane, chunk) block of the reduction
