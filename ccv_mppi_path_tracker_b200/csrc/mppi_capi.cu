@@ -82,6 +82,9 @@ struct mppi_handle_s {
   size_t last_h2d_bytes = 0;       // what the last upload / solve copied host -> device
   bool host_windows_staged = true; // the staged block carries host-built windows (must be copied)
   int opt_upload_warm_start = 1;   // mppi_solve copies the caller's u_nominal to the device (0: keeps the device's own)
+  float *d_window2 = nullptr;  // second slot of the device-built windows (the first one lives in d_in)
+  unsigned issue_idx = 0;      // stream-launched solves issued so far: its parity selects the slot
+  int last_slot = -1;          // slot of the last stream-launched solve
   float *h_out = nullptr, *d_out = nullptr;
   bool out_mapped = false;  // small results: the tail kernel writes them straight into the pinned host block
   size_t out_bytes = 0;
@@ -116,8 +119,12 @@ struct mppi_handle_s {
   int robot_offset = 0;
   // K0 (candidate grid) runs beside K1 (noise): they are independent
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_grid = nullptr, ev_join = nullptr, ev_readers = nullptr;
-  bool staged_recorded = false, readers_recorded = false;  // the events have been recorded on the current stream at least once
+  // ev_fork / ev_join_cap are only ever recorded inside a stream capture, the others only outside (an event whose
+  // last record was captured cannot be waited for by an ordinary stream operation)
+  cudaEvent_t ev_fork = nullptr, ev_join_cap = nullptr, ev_grid = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_readers[2] = {nullptr, nullptr};  // by slot: the last reader of that slot's window / grid / normals is done
+  bool readers_recorded[2] = {false, false};
+  bool staged_recorded = false, join_recorded = false;  // the events have been recorded at least once
   // graphs
   bool use_graph = false;
   cudaGraphExec_t exec_kernels = nullptr, exec_solve = nullptr;
@@ -266,7 +273,17 @@ bool fused_tail_for(mppi_handle h, const DeviceState &t) {
 //     prologue overlap the predecessor (pdl_wait() in the kernels).
 // The tail waits for K1: the generator reads the solve counter that the tail advances.
 int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
-  const DeviceState &d = h->d;
+  // Stream-launched solves alternate between two slots of window / grid (and, through the solve counter, of the
+  // normals), so that the side stream can prepare solve n+1 while K2 of solve n still reads its own slot; a graph
+  // always uses slot 0.
+  // (windows given by mppi_set_window live in the staging block, i.e. in slot 0 only: such handles stay there)
+  const bool alternate = !capturing && !(device_windows(h) && h->host_windows_staged);
+  const int slot = alternate ? (int)(h->issue_idx & 1u) : 0;
+  const int prev_slot = h->last_slot;  // slot of the previous stream-launched solve, -1: none
+  DeviceState d = h->d;
+  d.grid_hdr += (size_t)slot * d.R;
+  d.grid_cells += (size_t)slot * d.R * d.grid_max_cells;
+  if (slot && device_windows(h)) d.window = h->d_window2;
   DeviceState dp = d;  // launch descriptor for the kernels that may start under their predecessor
   dp.pdl = true;
   int n = 0;
@@ -277,13 +294,16 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   const bool pruned = scan == MPPI_SCAN_PRUNED;
   const bool side = pruned && (!capturing || prefetch);  // something runs on the side stream
   cudaStream_t gs = (pruned && !capturing) ? h->side_stream : s;  // where window builder and candidate grid run
+  // the normals of THIS solve were generated on the side stream during the previous one: K2 needs them complete
+  if (!capturing && h->join_recorded) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));
   if (side) {
     if (capturing) {
       CU_TRY(h, cudaEventRecord(h->ev_fork, s));
       CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     } else {
       if (h->staged_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->staged, 0));
-      if (h->readers_recorded) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_readers, 0));
+      // this slot's window and grid were last read two solves ago
+      if (h->readers_recorded[slot]) CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_readers[slot], 0));
     }
   }
   if (dev_win) {
@@ -295,8 +315,12 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
     ++n;
     if (!capturing) CU_TRY(h, cudaEventRecord(h->ev_grid, h->side_stream));
     if (prefetch) {
+      // the buffer of the next solve's normals was last read by the previous solve
+      if (!capturing && prev_slot >= 0 && prev_slot != slot)
+        CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_readers[prev_slot], 0));
       CU_TRY(h, launch_noise(d, 1, h->side_stream));
-      CU_TRY(h, cudaEventRecord(h->ev_join, h->side_stream));
+      CU_TRY(h, cudaEventRecord(capturing ? h->ev_join_cap : h->ev_join, h->side_stream));
+      if (!capturing) h->join_recorded = true;
       ++n;
     }
   }
@@ -321,28 +345,36 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
     ++n;
   }
   if (!capturing) {  // the last reader of this solve's window, grid and normals is queued
-    CU_TRY(h, cudaEventRecord(h->ev_readers, s));
-    h->readers_recorded = true;
+    CU_TRY(h, cudaEventRecord(h->ev_readers[slot], s));
+    h->readers_recorded[slot] = true;
+    h->last_slot = slot;
+    ++h->issue_idx;
   }
-  if (prefetch) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));  // join before the counter advances
+  // inside a graph the generator has to rejoin the capturing stream (it does not depend on the tail any more: it
+  // keeps its own solve index); with stream launches the NEXT solve's K2 waits for it (top of this function)
+  auto join = [&]() -> int {
+    if (capturing && prefetch) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join_cap, 0));
+    return MPPI_OK;
+  };
+  const DeviceState &dt = (capturing && !fused) ? dp : d;  // the tail directly behind K4: a programmatic dependent
   h->launch_count = n;
   if (fused) {  // rescale + finalize + merge (+ exchange) in one launch
     const int mode = h->p2p ? 1 : (h->n_ranks > 1 ? 2 : 0);
     CU_TRY(h, launch_rescale_tail(d, mode, s));
     h->launch_count = ++n;
-    if (mode != 2) return MPPI_OK;
+    if (mode != 2) return join();
   } else {
     if (h->p2p) {
-      CU_TRY(h, launch_finalize_exchange(d, s));
+      CU_TRY(h, launch_finalize_exchange(dt, s));
       h->launch_count = ++n;
-      return MPPI_OK;
+      return join();
     }
     if (fused_tail_for(h, d)) {
-      CU_TRY(h, launch_finalize_merge(d, s));
+      CU_TRY(h, launch_finalize_merge(dt, s));
       h->launch_count = ++n;
-      return MPPI_OK;
+      return join();
     }
-    CU_TRY(h, launch_finalize(d, s));
+    CU_TRY(h, launch_finalize(dt, s));
     ++n;
   }
   if (h->n_ranks > 1) {
@@ -354,7 +386,7 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   }
   CU_TRY(h, launch_merge(d, s));
   h->launch_count = ++n;
-  return MPPI_OK;
+  return join();
 }
 
 // Runs in front of a solve (outside any graph): with the prefetch on, the normals of the solve that is about to
@@ -368,6 +400,8 @@ int prime_noise(mppi_handle h, bool header_staged_only) {
     return MPPI_OK;
   }
   if (h->noise_primed) return MPPI_OK;
+  // a generator of an abandoned prefetch may still be running on the side stream (it advances its own solve index)
+  if (h->join_recorded) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   if (header_staged_only)  // the generator reads the shard offsets from the device header: bring it over first
     CU_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, kHeaderBytes, cudaMemcpyHostToDevice, h->stream));
   CU_TRY(h, launch_noise(h->d, 0, h->stream));
@@ -580,7 +614,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_grid, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  CU_NEW(cudaEventCreateWithFlags(&h->ev_readers, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_join_cap, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_readers[0], cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&h->ev_readers[1], cudaEventDisableTiming));
   CU_NEW(cudaDeviceGetAttribute(&h->sm_clock_khz, cudaDevAttrClockRate, device));
   if (h->sm_clock_khz <= 0) h->sm_clock_khz = 1965000;
   d.xchg_timeout_cycles = (long long)(h->opt_timeout_ms * (double)h->sm_clock_khz);
@@ -649,8 +685,9 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaMemset(d.tail_ticket, 0, sizeof(unsigned int) * ((size_t)d.R + 1)));
   CU_NEW(cudaMalloc((void **)&d.cmin, sizeof(unsigned int) * (size_t)d.R));
   CU_NEW(cudaMemset(d.cmin, 0xFF, sizeof(unsigned int) * (size_t)d.R));  // armed; every solve's tail re-arms it
-  CU_NEW(cudaMalloc((void **)&d.counter, sizeof(uint32_t)));
-  CU_NEW(cudaMemset(d.counter, 0, sizeof(uint32_t)));
+  // {solve counter, next solve the prefetching generator produces, the generator's last-block ticket, -}
+  CU_NEW(cudaMalloc((void **)&d.counter, 4 * sizeof(uint32_t)));
+  CU_NEW(cudaMemset(d.counter, 0, 4 * sizeof(uint32_t)));
   CU_NEW(cudaMemset(d.eps, 0, sizeof(float) * d.eps_buffers * d.eps_buf_elems));
   if (make_eps_tensor_map(d) != cudaSuccess) d.eps_map_valid = false;  // no TMA descriptor: the literal scan runs
   if (pruned_scan_supported(d.T, d.planes)) d.side_carveout = rollout_carveout_percent(d);
@@ -661,9 +698,13 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
       d.bounds.hi[u] = P0.u_max[u];
     }
   }
-  CU_NEW(cudaMalloc((void **)&d.grid_hdr, sizeof(GridHeader) * (size_t)d.R));
-  CU_NEW(cudaMemset(d.grid_hdr, 0, sizeof(GridHeader) * (size_t)d.R));
-  CU_NEW(cudaMalloc((void **)&d.grid_cells, sizeof(uint32_t) * (size_t)d.R * d.grid_max_cells));
+  // two slots of everything the side stream writes for the NEXT solve while K2 of the running one still reads its own:
+  // candidate grid (header + cells) and the device-built windows; back-to-back solves alternate between them
+  CU_NEW(cudaMalloc((void **)&d.grid_hdr, sizeof(GridHeader) * 2 * (size_t)d.R));
+  CU_NEW(cudaMemset(d.grid_hdr, 0, sizeof(GridHeader) * 2 * (size_t)d.R));
+  CU_NEW(cudaMalloc((void **)&d.grid_cells, sizeof(uint32_t) * 2 * (size_t)d.R * d.grid_max_cells));
+  CU_NEW(cudaMalloc((void **)&h->d_window2, sizeof(float) * (size_t)d.R * d.win_stride));
+  CU_NEW(cudaMemset(h->d_window2, 0, sizeof(float) * (size_t)d.R * d.win_stride));
   d.gathered = d.record;
 #undef CU_NEW
   h->path.resize(n_robots);
@@ -690,7 +731,7 @@ int mppi_destroy(mppi_handle h) {
   cudaFree(d.eps); cudaFree(d.cost); cudaFree(d.weight); cudaFree(d.wpart); cudaFree(d.npart);
   cudaFree(d.record); cudaFree(d.cta_part); cudaFree(d.tail_ticket); cudaFree(d.cmin); cudaFree(d.counter);
   cudaFree(d.nearest);
-  cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg);
+  cudaFree(d.grid_hdr); cudaFree(d.grid_cells); cudaFree(d.states_dbg); cudaFree(h->d_window2);
   cudaFree(h->d_path); cudaFree(h->d_path_off); cudaFree(h->d_win_fixed); cudaFree(d.cur_index);
   cudaFree(h->d_in);
   if (!h->out_mapped) cudaFree(h->d_out);
@@ -700,7 +741,9 @@ int mppi_destroy(mppi_handle h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_grid) cudaEventDestroy(h->ev_grid);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->ev_readers) cudaEventDestroy(h->ev_readers);
+  if (h->ev_join_cap) cudaEventDestroy(h->ev_join_cap);
+  for (auto &e : h->ev_readers)
+    if (e) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -762,7 +805,8 @@ int mppi_set_option(mppi_handle h, int option, double value) {
       CU_TRY(h, cudaSetDevice(h->device));
       CU_TRY(h, cudaStreamSynchronize(h->stream));
       uint32_t *cells = nullptr;
-      CU_TRY(h, cudaMalloc((void **)&cells, sizeof(uint32_t) * (size_t)d.R * (size_t)iv));
+      if (h->side_stream) CU_TRY(h, cudaStreamSynchronize(h->side_stream));
+      CU_TRY(h, cudaMalloc((void **)&cells, sizeof(uint32_t) * 2 * (size_t)d.R * (size_t)iv));
       cudaFree(d.grid_cells);
       d.grid_cells = cells;
       d.grid_max_cells = (int)iv;
@@ -953,6 +997,7 @@ int mppi_enqueue(mppi_handle h) {
       rc = capture(h, false, &h->exec_kernels);
       if (rc) return rc;
     }
+    if (h->join_recorded) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));  // a generator from a stream-launched solve
     CU_TRY(h, cudaGraphLaunch(h->exec_kernels, h->stream));
     h->weights_valid = !h->last_fused;  // a replay overwrites the costs: weights of an earlier solve are stale
     return MPPI_OK;
@@ -999,6 +1044,7 @@ int mppi_solve(mppi_handle h, const double *state, double dt, double *u_nominal)
       rc = capture(h, true, &h->exec_solve);
       if (rc) return rc;
     }
+    if (h->join_recorded) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     CU_TRY(h, cudaGraphLaunch(h->exec_solve, h->stream));
     h->weights_valid = !h->last_fused;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1172,6 +1218,7 @@ int mppi_time_kernels(mppi_handle h, int n_iters, float *ms) {
   bool want_nearest;
   const int scan = effective_scan(h, &want_nearest);
   h->noise_primed = false;  // the generator runs in front of its own solve here
+  if (h->join_recorded) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_join, 0));  // a prefetching generator still in flight
   for (int it = 0; it <= n_iters; ++it) {
     if (device_windows(h)) CU_TRY(h, launch_window_builder(d, s));
     CU_TRY(h, cudaEventRecord(ev[0], s));

@@ -23,8 +23,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// block-level min of the per-thread costs, one atomicMin per block; returns the block's minimum to every thread
-// (INFINITY when no thread is valid)
+// block-level min of the per-thread costs, one atomicMin per block (cmin_slot may be null: none); returns the block's
+// minimum to every thread (INFINITY when no thread is valid)
 __device__ __forceinline__ float block_min_to_global(float c, bool valid, unsigned int *cmin_slot, float *s_red) {
   float v = valid ? c : INFINITY;
   v = warp_min(v);
@@ -34,7 +34,7 @@ __device__ __forceinline__ float block_min_to_global(float c, bool valid, unsign
   const int nw = (blockDim.x + 31) >> 5;
   float m = lane < nw ? s_red[lane] : INFINITY;
   m = warp_min(m);
-  if (wid == 0 && lane == 0 && m < INFINITY) atomicMin(cmin_slot, float_to_ordered(m));
+  if (cmin_slot && wid == 0 && lane == 0 && m < INFINITY) atomicMin(cmin_slot, float_to_ordered(m));
   return m;
 }
 
