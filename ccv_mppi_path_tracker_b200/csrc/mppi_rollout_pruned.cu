@@ -851,30 +851,61 @@ __device__ __forceinline__ float sum_fixed(const float (&a)[B]) {
   return s[0];
 }
 
-// column `col` of the rescaled sum over nc CTA records of one robot (col 1: S, col 2: Q, col >= 4: N[col - 4]);
-// B loads of the minima + B loads of the column in flight per thread
+// One batch of a record column: B loads in flight per thread (rows c .. c+B-1 of the block's group; the rows past the
+// group repeat its last record and get the weight 0 below)
 template <int B>
-__device__ __forceinline__ float fold_records(const float *__restrict__ part, int part_stride, int nc, int col,
-                                              float c_min, float inv_lambda) {
-  float acc[B];
+__device__ __forceinline__ void load_batch(float (&v)[B], const float *__restrict__ part, int part_stride, int nc,
+                                           int c, int col) {
 #pragma unroll
-  for (int k = 0; k < B; ++k) acc[k] = 0.f;
-  for (int c = 0; c < nc; c += B) {
-    float m[B], v[B];
+  for (int k = 0; k < B; ++k) v[k] = part[(size_t)min(c + k, nc - 1) * part_stride + col];
+}
+// acc[k] += a_c * v[k] with the records' rescale factors a_c from shared memory (a_c^2 for the Q column)
+template <int B>
+__device__ __forceinline__ void fma_batch(float (&acc)[B], const float (&v)[B], const float *s_a, int nc, int c,
+                                          bool squared) {
 #pragma unroll
-    for (int k = 0; k < B; ++k) {
-      const float *rec = part + (size_t)min(c + k, nc - 1) * part_stride;
-      m[k] = rec[0];  // the same address for every thread of the block: one broadcast request
-      v[k] = rec[col];
-    }
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      float a = c + k < nc ? expf(-(m[k] - c_min) * inv_lambda) : 0.f;
-      if (col == 2) a *= a;
-      acc[k] = fmaf(a, v[k], acc[k]);
-    }
+  for (int k = 0; k < B; ++k) {
+    float a = c + k < nc ? s_a[c + k] : 0.f;
+    if (squared) a *= a;
+    acc[k] = fmaf(a, v[k], acc[k]);
   }
-  return sum_fixed<B>(acc);
+}
+
+// Every column of the rescaled sum over the nc CTA records of the block's group (col 1: S, col 2: Q, col >= 4:
+// N[col - 4]; columns 0 and 3 are 0), one thread per column.  The factors a_c = exp(-(m_c - c_min)/lambda) are
+// computed ONCE per record (thread c) into shared memory -- not once per (record, column) -- while the first batch of
+// every thread's column is already in flight: the block's first L2 round trip carries both.  All threads of the block
+// must call it (it contains a barrier).  Results: column threadIdx.x in out0, threadIdx.x + blockDim.x in out1,
+// further ones only through gp (when non-null every column is stored there).
+template <int B>
+__device__ __forceinline__ void fold_group(const float *__restrict__ part, int part_stride, int nc, int ncol,
+                                           const unsigned int *__restrict__ cmin_slot, float inv_lambda, float *s_a,
+                                           float *__restrict__ gp, float &c_min_out, float &out0, float &out1) {
+  const int col0 = threadIdx.x;
+  const bool live0 = col0 < ncol && col0 != 0 && col0 != 3;
+  float v[B];
+  if (live0) load_batch<B>(v, part, part_stride, nc, 0, col0);
+  const float c_min = ordered_to_float(*cmin_slot);
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) s_a[c] = expf(-(part[(size_t)c * part_stride] - c_min) * inv_lambda);
+  __syncthreads();
+  c_min_out = c_min;
+  int slot = 0;
+  for (int col = threadIdx.x; col < ncol; col += blockDim.x, ++slot) {
+    float r = 0.f;
+    if (col != 0 && col != 3) {
+      float acc[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) acc[k] = 0.f;
+      for (int c = 0; c < nc; c += B) {
+        if (slot != 0 || c != 0) load_batch<B>(v, part, part_stride, nc, c, col);
+        fma_batch<B>(acc, v, s_a, nc, c, col == 2);
+      }
+      r = sum_fixed<B>(acc);
+    }
+    if (gp) gp[col] = r;
+    if (slot == 0) out0 = r;
+    else if (slot == 1) out1 = r;
+  }
 }
 
 template <int MODE>
@@ -885,28 +916,23 @@ __global__ void __launch_bounds__(256)
                         uint32_t *__restrict__ counter, unsigned int *__restrict__ ticket, int planes, int n_cta,
                         int part_stride, int groups, int per, int R, ExchangeArgs x) {
   __shared__ float s_S;
+  __shared__ float s_a[kRescaleMaxCtas];  // rescale factors of the block's CTA records
   const int robot = blockIdx.y, g = blockIdx.x;
   const int ncol = 4 + planes;
-  const float c_min = ordered_to_float(cmin[robot]);
-  const float inv_lambda = hdr->inv_lambda;
+  const float inv_lambda = hdr->inv_lambda;  // an input of the solve
   const int c0 = g * per, nc = min(per, n_cta - c0);
   const float *part = cta_part + ((size_t)robot * n_cta + c0) * part_stride;
   float *rec = record + (size_t)robot * part_stride;
   // many-robot handles: one block owns the robot and (record columns <= 2 per thread) nothing leaves its registers
   const bool in_regs = ncol <= 2 * (int)blockDim.x;
   const bool single_regs = groups == 1 && in_regs;
-  float *gp = gpart + ((size_t)robot * groups + g) * part_stride;
+  float *gp = single_regs ? nullptr : gpart + ((size_t)robot * groups + g) * part_stride;
   float mine0 = 0.f, mine1 = 0.f;  // this thread's (up to two) columns
+  float c_min;
   int slot = 0;
-  for (int col = threadIdx.x; col < ncol; col += blockDim.x, ++slot) {
-    float v = 0.f;
-    if (col != 0 && col != 3)
-      v = nc <= 8 ? fold_records<8>(part, part_stride, nc, col, c_min, inv_lambda)
-                  : fold_records<kTailMlp>(part, part_stride, nc, col, c_min, inv_lambda);
-    if (!single_regs) gp[col] = v;
-    else if (slot == 0) mine0 = v;
-    else mine1 = v;
-  }
+  pdl_wait();  // the CTA records and the minimum come from K2, the kernel in front
+  if (nc <= 8) fold_group<8>(part, part_stride, nc, ncol, cmin + robot, inv_lambda, s_a, gp, c_min, mine0, mine1);
+  else fold_group<kTailMlp>(part, part_stride, nc, ncol, cmin + robot, inv_lambda, s_a, gp, c_min, mine0, mine1);
   if (!single_regs) {
     if (!last_block_of_grid(ticket + 1 + robot, gridDim.x)) return;
   } else {
@@ -993,9 +1019,10 @@ cudaError_t launch_rescale_tail(const DeviceState &d, int mode, cudaStream_t s) 
   float *nominal = d.feedback ? d.nominal : nullptr;
   ExchangeArgs x = exchange_args(d);
 #define MPPI_LAUNCH_TAIL(M)                                                                                          \
-  rescale_tail_kernel<M><<<grid, 256, 0, s>>>(d.hdr, d.cta_part, d.cmin, d.npart, d.record, d.u_new, nominal, d.stats, \
-                                              d.counter, d.tail_ticket, d.planes, n_cta, d.rec_stride, groups, per,  \
-                                              d.R, x)
+  le = launch_kernel(d.pdl, rescale_tail_kernel<M>, grid, dim3(256), 0, s, d.hdr, d.cta_part, d.cmin, d.npart,       \
+                     d.record, d.u_new, nominal, d.stats, d.counter, d.tail_ticket, d.planes, n_cta, d.rec_stride,   \
+                     groups, per, d.R, x)
+  cudaError_t le;
   if (mode == 0) {
     MPPI_LAUNCH_TAIL(0);
   } else if (mode == 1) {
@@ -1003,6 +1030,7 @@ cudaError_t launch_rescale_tail(const DeviceState &d, int mode, cudaStream_t s) 
   } else {
     MPPI_LAUNCH_TAIL(2);
   }
+  if (le != cudaSuccess) return le;
 #undef MPPI_LAUNCH_TAIL
   return cudaGetLastError();
 }

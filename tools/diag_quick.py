@@ -17,6 +17,9 @@ def main():
     cases = [("diff_drive", 1 << 20, 100, 1), ("diff_drive", 1 << 19, 100, 1), ("diff_drive", 1 << 17, 100, 1),
              ("diff_drive", 1 << 16, 100, 1), ("full_body", 16384, 100, 1), ("steering", 4096, 50, 1),
              ("diff_drive", 1024, 50, 1024)]
+    only = os.environ.get("DIAG_CASES")  # e.g. "0,2,6": indices into the list above
+    if only:
+        cases = [cases[int(i)] for i in only.split(",")]
     opts = [a.split("=") for a in sys.argv[1:]]
     for model, K, T, R in cases:
         U = bench.NUM_CONTROLS[model]
