@@ -542,6 +542,10 @@ int copy_out(mppi_handle h, double *u_nominal) {
 
 }  // namespace
 
+#ifndef MPPI_MAPPED_OUT_BYTES
+#define MPPI_MAPPED_OUT_BYTES (1 << 20)
+#endif
+
 extern "C" {
 
 int mppi_abi_version(void) { return MPPI_B200_ABI_VERSION; }
@@ -644,10 +648,11 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   memset(h->h_out, 0, h->out_bytes);
   CU_NEW(cudaMalloc((void **)&h->d_in, h->in_bytes));
   CU_NEW(cudaMemset(h->d_in, 0, h->in_bytes));
-  // Results of up to 16 KB (single robots: (T-1) x U controls + 4 statistics) need no device copy and no D2H node:
-  // the pinned block is addressable from the device (unified addressing), the tail kernel stores into it over PCIe
-  // and the host reads it after the stream synchronisation it does anyway.  Fleets keep the device buffer + one copy.
-  h->out_mapped = h->out_bytes <= 16 * 1024;
+  // Results of up to 1 MB ((T-1) x U controls + 4 statistics per robot; 1024 robots at T = 50: 418 KB) need no device
+  // copy and no D2H node: the pinned block is addressable from the device (unified addressing), the tail kernel stores
+  // into it over PCIe (posted writes, nothing on the device reads them back) and the host reads it after the stream
+  // synchronisation it does anyway.  Larger fleets keep the device buffer + one copy.
+  h->out_mapped = h->out_bytes <= (size_t)MPPI_MAPPED_OUT_BYTES;
   if (h->out_mapped) {
     h->d_out = h->h_out;
   } else {
