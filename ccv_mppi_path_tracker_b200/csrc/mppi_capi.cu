@@ -273,6 +273,9 @@ bool fused_tail_for(mppi_handle h, const DeviceState &t) {
 //     K2, K3, K4 are programmatic dependents of the kernel in front of them: their launch latency and K2's input
 //     prologue overlap the predecessor (pdl_wait() in the kernels).
 // The tail waits for K1: the generator reads the solve counter that the tail advances.
+#ifndef MPPI_K2_STREAM_PDL
+#define MPPI_K2_STREAM_PDL 1
+#endif
 int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   // Stream-launched solves alternate between two slots of window / grid (and, through the solve counter, of the
   // normals), so that the side stream can prepare solve n+1 while K2 of solve n still reads its own slot; a graph
@@ -331,8 +334,10 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
   }
   if (pruned && !capturing) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_grid, 0));
   const bool fused = fused_controls(h, scan);
-  // K2 directly behind K0 on the same stream (graph, no generator in between): a programmatic dependent
-  const bool k2_pdl = pruned && capturing && (h->external_noise || prefetch);
+  // K2 directly behind K0 on the same stream (graph, no generator in between): a programmatic dependent.  With stream
+  // launches it follows the previous solve's tail (event waits in between): its CTAs load header and window and set
+  // up their barriers while that tail still runs, and read warm start, counter and grid only after it.
+  const bool k2_pdl = pruned && (h->external_noise || prefetch) && (capturing || MPPI_K2_STREAM_PDL);
   CU_TRY(h, launch_rollout_cost(k2_pdl ? dp : d, scan, want_nearest, want_states, fused, s));
   ++n;
   h->last_fused = fused;

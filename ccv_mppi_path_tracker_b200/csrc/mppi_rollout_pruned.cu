@@ -771,7 +771,8 @@ __global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB
 
   const float *g_win = window + (size_t)robot * win_stride;
   pdl_trigger();  // the reduction kernel behind may be launched; it waits for this grid before it reads a cost
-  // inputs of the solve (header, window, warm start): ready before the candidate grid in front of this kernel started
+  // Inputs of the solve that were complete before the kernel in front of this one was launched (header, window): the
+  // kernel in front is the candidate grid (graph) or the previous solve's tail (stream launches).
   load_params_to_shared(&sP, hdr);
   if (threadIdx.x < 4 * kStages) mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[threadIdx.x]), 1u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -780,9 +781,9 @@ __global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB
     const int j0 = min(2 * q, T - 1), j1 = min(2 * q + 1, T - 1);
     s_pairs[q] = make_float4(g_win[2 * j0], g_win[2 * j1], g_win[2 * j0 + 1], g_win[2 * j1 + 1]);
   }
+  pdl_wait();  // the candidate grid (K0) / the previous solve's warm start, counter and minimum slot are complete
   for (int j = threadIdx.x; j < planes + 2 * U; j += blockDim.x)
     s_nom[j] = j < planes ? nominal[(size_t)robot * planes + j] : 0.f;
-  pdl_wait();  // the candidate grid (K0) is complete and visible from here on
   if (threadIdx.x == 0) s_gh = ghdr[robot];
   __syncthreads();
 
@@ -930,7 +931,8 @@ __global__ void __launch_bounds__(256)
   float mine0 = 0.f, mine1 = 0.f;  // this thread's (up to two) columns
   float c_min;
   int slot = 0;
-  pdl_wait();  // the CTA records and the minimum come from K2, the kernel in front
+  pdl_wait();     // the CTA records and the minimum come from K2, the kernel in front
+  pdl_trigger();  // the next solve's K2 may bring its CTAs onto the SMs (header, window -> shared memory) meanwhile
   if (nc <= 8) fold_group<8>(part, part_stride, nc, ncol, cmin + robot, inv_lambda, s_a, gp, c_min, mine0, mine1);
   else fold_group<kTailMlp>(part, part_stride, nc, ncol, cmin + robot, inv_lambda, s_a, gp, c_min, mine0, mine1);
   if (!single_regs) {
