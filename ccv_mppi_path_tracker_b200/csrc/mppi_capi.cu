@@ -85,7 +85,6 @@ struct mppi_handle_s {
   float *d_window2 = nullptr;  // second slot of the device-built windows (the first one lives in d_in)
   unsigned issue_idx = 0;      // stream-launched solves issued so far: its parity selects the slot
   int last_slot = -1;          // slot of the last stream-launched solve
-  int sm_count = 148;
   float *h_out = nullptr, *d_out = nullptr;
   bool out_mapped = false;  // small results: the tail kernel writes them straight into the pinned host block
   size_t out_bytes = 0;
@@ -370,8 +369,7 @@ int issue_kernels(mppi_handle h, cudaStream_t s, bool capturing) {
     // the SMs, the solve's constants loaded, when K2's last CTA retires (K = 2^17: 91.3 -> 90.5 us per solve, 2^16:
     // 61.7 -> 58.9).  Behind a K2 of several waves the parked blocks only take SM room from the side stream's
     // generator (K = 2^20: 0.515 -> 0.522 ms; 1024 robots: 0.376 -> 0.385 ms): an ordinary launch there.
-    const bool one_wave = (long long)d.R * ((d.K + 127) / 128) <= (long long)8 * h->sm_count;
-    CU_TRY(h, launch_rescale_tail(one_wave ? dp : d, mode, s));
+    CU_TRY(h, launch_rescale_tail(rollout_is_one_wave(d) ? dp : d, mode, s));
     h->launch_count = ++n;
     if (mode != 2) return join();
   } else {
@@ -633,7 +631,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
   CU_NEW(cudaEventCreateWithFlags(&h->ev_readers[0], cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&h->ev_readers[1], cudaEventDisableTiming));
   CU_NEW(cudaDeviceGetAttribute(&h->sm_clock_khz, cudaDevAttrClockRate, device));
-  CU_NEW(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CU_NEW(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
   if (h->sm_clock_khz <= 0) h->sm_clock_khz = 1965000;
   d.xchg_timeout_cycles = (long long)(h->opt_timeout_ms * (double)h->sm_clock_khz);
 

@@ -99,6 +99,7 @@ struct DeviceState {
   int k4_groups = 0;  // > 0: plane groups per K4 block (tuning); else by the number of blocks
   unsigned int *tail_ticket = nullptr;  // [R + 1] "last block" tickets of the one-kernel tail (fused-controls path)
   bool pdl = false;           // launch K2 / K3 / K4 as programmatic dependents of the kernel in front of them
+  int sm_count = 148;         // SMs of the device (cudaDevAttrMultiProcessorCount)
   int side_carveout = -1;     // shared-memory carve-out (per cent) given to the side-stream kernels: K2's own
   ControlBounds bounds = {};  // kernel parameter of K2 (kept equal to hdr->P.u_min / u_max by the host)
   bool eps_map_valid = false;
@@ -128,6 +129,11 @@ inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// K2 (128-thread CTAs, 8 resident per SM by registers) fits the machine in a single wave
+inline bool rollout_is_one_wave(const DeviceState &d) {
+  return (long long)d.R * ((d.K + 127) / 128) <= (long long)8 * d.sm_count;
 }
 
 constexpr int kHeaderBytes = 256;
