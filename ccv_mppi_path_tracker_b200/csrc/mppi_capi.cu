@@ -91,6 +91,7 @@ struct mppi_handle_s {
   // host-side per-robot inputs
   std::vector<std::vector<double>> path;
   std::vector<char> window_fixed;
+  std::vector<char> window_yaw_stale;  // the host-built window's yaw_ref column still has to be derived (mppi_get_window)
   std::vector<double> window;  // [R][T][3]
   std::vector<int> cur_index;
   bool have_inputs = false, have_nominal = false;
@@ -457,9 +458,11 @@ int stage_inputs(mppi_handle h, const double *state, double dt, const double *u_
     double *w = h->window.data() + (size_t)r * h->T * 3;
     if (!h->window_fixed[r]) {
       if (h->path[r].empty()) return fail(h, MPPI_ERR_STATE, "no path or window set for robot " + std::to_string(r));
-      if (!on_device)
+      if (!on_device) {  // x, y only: the yaw column is filled in when mppi_get_window asks for it
         h->cur_index[r] = calc_ref_path(h->path[r].data(), (int)(h->path[r].size() / 2), s[0], s[1], h->params.v_ref,
-                                        dt, h->params.resolution, h->T, w);
+                                        dt, h->params.resolution, h->T, w, false);
+        h->window_yaw_stale[r] = 1;
+      }
     }
     // windows built on the device (K-1) overwrite this robot's slot after the H2D copy
     if (!on_device || h->window_fixed[r]) {
@@ -724,6 +727,7 @@ int mppi_create(mppi_handle *out, int model, const mppi_params *params, int num_
 #undef CU_NEW
   h->path.resize(n_robots);
   h->window_fixed.assign(n_robots, 0);
+  h->window_yaw_stale.assign(n_robots, 0);
   h->window.assign((size_t)n_robots * horizon * 3, 0.0);
   h->cur_index.assign(n_robots, 0);
   h->last_state.assign((size_t)n_robots * h->S, 0.0);
@@ -910,6 +914,7 @@ int mppi_set_window(mppi_handle h, int robot, const double *window_xyyaw) {
   if (robot < 0 || robot >= h->R || !window_xyyaw) return fail(h, MPPI_ERR_INVALID, "bad robot index or NULL window");
   memcpy(h->window.data() + (size_t)robot * h->T * 3, window_xyyaw, sizeof(double) * 3 * (size_t)h->T);
   h->window_fixed[robot] = 1;
+  h->window_yaw_stale[robot] = 0;
   h->cur_index[robot] = 0;
   h->paths_dirty = true;
   return MPPI_OK;
@@ -1167,6 +1172,10 @@ int mppi_get_window(mppi_handle h, int robot, double *window_xyyaw, int *current
     h->cur_index[robot] = cur;
     window_from_index(h->path[robot].data(), (int)(h->path[robot].size() / 2), cur, h->params.v_ref, h->last_dt,
                       h->params.resolution, h->T, h->window.data() + (size_t)robot * h->T * 3);
+  }
+  if (h->window_yaw_stale[robot]) {
+    window_yaw(h->T, h->window.data() + (size_t)robot * h->T * 3);
+    h->window_yaw_stale[robot] = 0;
   }
   if (window_xyyaw) memcpy(window_xyyaw, h->window.data() + (size_t)robot * h->T * 3, sizeof(double) * 3 * (size_t)h->T);
   if (current_index) *current_index = h->cur_index[robot];

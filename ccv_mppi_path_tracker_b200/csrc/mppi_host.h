@@ -62,8 +62,15 @@ inline int current_index(const double *path_xy, int n, double px, double py) {
 
 // calc_RefPath after get_CurrentIndex: DD:160-181.  window = T x {x_ref, y_ref, yaw_ref}; yaw_ref[T-1] = 0 (never
 // written, DD:44).
+// with_yaw = false leaves the yaw_ref column as it is (window_yaw fills it in later): the kernels take yaw_ref[0]
+// from the FP32 window, so the T-1 atan2 calls are only needed when somebody asks for the window itself.
+inline void window_yaw(int T, double *window) {  // DD:175-178
+  for (int i = 0; i + 1 < T; ++i)
+    window[3 * i + 2] = atan2(window[3 * (i + 1) + 1] - window[3 * i + 1], window[3 * (i + 1)] - window[3 * i]);
+  if (T > 0) window[3 * (T - 1) + 2] = 0.0;
+}
 inline void window_from_index(const double *path_xy, int n, int cur, double v_ref, double dt, double resolution, int T,
-                              double *window) {
+                              double *window, bool with_yaw = true) {
   const double step = v_ref * dt / resolution;  // DD:160
   for (int i = 0; i < T; ++i) {
     int index = (int)(cur + i * step);  // DD:163 truncation of a double
@@ -75,16 +82,14 @@ inline void window_from_index(const double *path_xy, int n, int cur, double v_re
       window[3 * i + 1] = path_xy[2 * index + 1];
     }
   }
-  for (int i = 0; i + 1 < T; ++i)
-    window[3 * i + 2] = atan2(window[3 * (i + 1) + 1] - window[3 * i + 1], window[3 * (i + 1)] - window[3 * i]);
-  if (T > 0) window[3 * (T - 1) + 2] = 0.0;
+  if (with_yaw) window_yaw(T, window);
 }
 
 // calc_RefPath: DD:156-181
 inline int calc_ref_path(const double *path_xy, int n, double px, double py, double v_ref, double dt,
-                         double resolution, int T, double *window) {
+                         double resolution, int T, double *window, bool with_yaw = true) {
   const int cur = current_index(path_xy, n, px, py);
-  window_from_index(path_xy, n, cur, v_ref, dt, resolution, T, window);
+  window_from_index(path_xy, n, cur, v_ref, dt, resolution, T, window, with_yaw);
   return cur;
 }
 

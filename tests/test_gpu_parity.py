@@ -898,6 +898,39 @@ def test_noise_prefetch_is_bit_identical(model, K, T, R):
         assert np.array_equal(runs[mode][0], ref[0]), mode
 
 
+@pytest.mark.parametrize("model,K,T,R", [("diff_drive", 40000, 60, 1),   # fused controls, K2 a single wave: the tail and
+                                                                            # the next K2 are programmatic dependents
+                                         ("diff_drive", 200000, 40, 1),  # fused controls, K2 of several waves
+                                         ("steering", 4096, 50, 1),      # K3 + K4 + one-block finalize
+                                         ("diff_drive", 600, 50, 9)])    # device-built windows, one-block tails
+def test_back_to_back_enqueues_equal_synchronous_solves(model, K, T, R):
+    """Six solves enqueued without a host synchronisation in between -- the next solve's K2 is resident under the
+    running tail (programmatic dependent launch), window builder / candidate grid / generator of solve n+1 run on the
+    side stream under solve n, two slots of window and grid alternate -- give the controls, costs and noise of six
+    solves the host waits for one by one, bit for bit (warm start fed back on the device, DD:89-90)."""
+    case = make_case(model, K, T, seed=43)
+    states = np.tile(case["state"], (R, 1))
+    states[:, 1] += 0.02 * np.arange(R)
+    runs = {}
+    for mode in ("sync", "back_to_back", "graph"):
+        with _make_ctl(case, n_robots=R) as ctl:
+            ctl.set_seed(99, 5)
+            ctl.optimal_solution[...] = case["u0"]
+            ctl.use_graph(mode == "graph")
+            ctl.upload(states, case["dt"], with_nominal=True)
+            for it in range(6):
+                ctl.enqueue()
+                if mode == "sync":
+                    ctl.synchronize()
+            u = ctl.download().copy()
+            runs[mode] = (u, ctl.costs(R - 1), ctl.noise(R - 1), ctl.stats(R - 1)["c_min"])
+    for mode in ("back_to_back", "graph"):
+        assert np.array_equal(runs[mode][2], runs["sync"][2]), mode
+        assert np.array_equal(runs[mode][1].view(np.uint32), runs["sync"][1].view(np.uint32)), mode
+        assert np.array_equal(runs[mode][0], runs["sync"][0]), mode
+        assert runs[mode][3] == runs["sync"][3], mode
+
+
 def test_weights_tap_after_graph_replays_on_the_fused_path():
     """mppi_get_weights on the fused-controls path recomputes the weights on demand; a CUDA-graph replay must
     invalidate an earlier on-demand result (it used to return the previous solve's weights)."""
