@@ -79,20 +79,6 @@ __device__ __forceinline__ unsigned long long *xchg_slot(void *base, int parity,
 __device__ __forceinline__ unsigned long long xchg_pack(float v, unsigned int stamp) {
   return ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(v);
 }
-// spins until the word carries `stamp`; returns false on time-out
-__device__ __forceinline__ bool xchg_poll(const unsigned long long *word, unsigned int stamp, long long t0,
-                                          long long timeout_cycles, float &payload) {
-  const volatile unsigned long long *w = word;
-  for (;;) {
-    const unsigned long long v = *w;
-    if ((unsigned int)(v >> 32) == stamp) {
-      payload = __uint_as_float((unsigned int)v);
-      return true;
-    }
-    if (clock64() - t0 > timeout_cycles) return false;
-  }
-}
-
 constexpr int kExchangeRegRanks = 8;  // ranks whose records the merging block keeps in registers (one robot)
 
 // The exchange step of a sample-sharded solve, run by ONE block once this rank's records [R][rec_stride] are complete
@@ -129,15 +115,35 @@ __device__ __forceinline__ void exchange_and_merge(const SolveHeader *__restrict
       if (has0) *reinterpret_cast<volatile unsigned long long *>(dst + k0) = xchg_pack(v0, stamp);
       if (has1) *reinterpret_cast<volatile unsigned long long *>(dst + k1) = xchg_pack(v1, stamp);
     }
+    // Poll all ranks' words of this thread TOGETHER: one batch of (up to) 2 G independent loads per trip, repeated
+    // until every stamp matches.  (Polling word after word -- each a loop of its own -- cost one L2 round trip per
+    // word even when everything had arrived: 2 G dependent trips, ~10 us at G = 8.)
     float a0[kExchangeRegRanks], a1[kExchangeRegRanks];
     bool ok = true;
+    {
+      const volatile unsigned long long *src0 = xchg_slot(x.xbuf, parity, 0, G, slot_elems);
+      for (;;) {
+        unsigned long long w0[kExchangeRegRanks], w1[kExchangeRegRanks];
 #pragma unroll
-    for (int g = 0; g < kExchangeRegRanks; ++g) {
-      a0[g] = a1[g] = 0.f;
-      if (g < G) {
-        const unsigned long long *src = xchg_slot(x.xbuf, parity, g, G, slot_elems);
-        if (has0) ok = xchg_poll(src + k0, stamp, t0, x.timeout_cycles, a0[g]) && ok;
-        if (has1) ok = xchg_poll(src + k1, stamp, t0, x.timeout_cycles, a1[g]) && ok;
+        for (int g = 0; g < kExchangeRegRanks; ++g) {
+          w0[g] = w1[g] = (unsigned long long)stamp << 32;
+          if (g < G) {
+            if (has0) w0[g] = src0[(size_t)g * slot_elems + k0];
+            if (has1) w1[g] = src0[(size_t)g * slot_elems + k1];
+          }
+        }
+        bool all = true;
+#pragma unroll
+        for (int g = 0; g < kExchangeRegRanks; ++g) {
+          all = all && (unsigned int)(w0[g] >> 32) == stamp && (unsigned int)(w1[g] >> 32) == stamp;
+          a0[g] = __uint_as_float((unsigned int)w0[g]);
+          a1[g] = __uint_as_float((unsigned int)w1[g]);
+        }
+        if (all) break;
+        if (clock64() - t0 > x.timeout_cycles) {
+          ok = false;
+          break;
+        }
       }
     }
     if (!ok) s_timeout = 1;
@@ -196,11 +202,24 @@ __device__ __forceinline__ void exchange_and_merge(const SolveHeader *__restrict
         *reinterpret_cast<volatile unsigned long long *>(xchg_slot(x.peers[g], parity, x.rank, G, slot_elems) + k) =
             xchg_pack(v, stamp);
     }
+    // poll the words of eight ranks at a time (independent loads: one L2 round trip per batch once they have arrived)
     bool ok = true;
-    for (size_t k = threadIdx.x; k < slot_elems; k += blockDim.x)
-      for (int g = 0; g < G; ++g) {
-        float unused;
-        ok = xchg_poll(xchg_slot(x.xbuf, parity, g, G, slot_elems) + k, stamp, t0, x.timeout_cycles, unused) && ok;
+    for (size_t k = threadIdx.x; k < slot_elems && ok; k += blockDim.x)
+      for (int g0 = 0; g0 < G && ok; g0 += 8) {
+        const volatile unsigned long long *src = xchg_slot(x.xbuf, parity, g0, G, slot_elems) + k;
+        for (;;) {
+          bool all = true;
+          unsigned long long w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = g0 + j < G ? src[(size_t)j * slot_elems] : (unsigned long long)stamp << 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) all = all && (unsigned int)(w[j] >> 32) == stamp;
+          if (all) break;
+          if (clock64() - t0 > x.timeout_cycles) {
+            ok = false;
+            break;
+          }
+        }
       }
     if (!ok) s_timeout = 1;
   }
