@@ -657,9 +657,9 @@ __device__ __forceinline__ float rollout_thread_tma(const ThreadCtx &cx, const T
 // shadow of the other CTAs' rollouts (K2 uses a quarter of the HBM bandwidth) -- instead of a separate pass of
 // the whole tensor through HBM.  Not inlined (called once per thread, keeps the rollout loop's code compact).
 template <int MODEL>
-__device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float inv_lambda, float c, bool valid,
-                                                   float m_cta, const float *s_nom, const float *eps_robot, int Kp,
-                                                   int planes, float *rec) {
+__device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float4 bounds01, float inv_lambda, float c,
+                                                   bool valid, float m_cta, const float *s_nom,
+                                                   const float *eps_robot, int Kp, int planes, float *rec) {
   constexpr int U = MODEL == kDiffDrive ? 2 : (MODEL == kSteering ? 3 : 5);
   __shared__ __align__(16) float s_w[128];
   __shared__ float s_sq[2][4];
@@ -681,11 +681,13 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float 
     rec[3] = 0.f;
   }
   const float4 wq = *reinterpret_cast<const float4 *>(&s_w[4 * lane]);  // weights of samples 4*lane .. 4*lane+3
-  const int s0 = blockIdx.x * 128 + 4 * lane;                          // first of this lane's four samples
-  const bool in_range = s0 < Kp;                                        // Kp is a multiple of 4
+  // first of this lane's four samples; lanes past the (padded) sample count read the last quad instead -- their four
+  // weights are 0 (samples >= K), so what they load does not matter and the loads need no predicate (Kp is a multiple of 4)
+  const int s0 = min(blockIdx.x * 128 + 4 * lane, Kp - 4);
   const float *e_base = eps_robot + s0;
   const float sigma = sP.sigma;
   const bool steer_off = MODEL == kFullBody && sP.steer_off;
+  const float4 *s_nom4 = reinterpret_cast<const float4 *>(s_nom);  // 16-byte aligned, padded by 2 U >= 4 entries
   // a warp takes 4 consecutive planes at a time: 4 independent 16-byte loads per lane, then one transposing butterfly
   // reduces the 4 partial sums over the 32 lanes (lanes 0, 8, 16, 24 end up with one plane each); fixed order,
   // deterministic.  (Issuing the next four planes' loads ahead of the arithmetic, or 8 planes at a time, costs 12-18
@@ -695,14 +697,20 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int p = min(p0 + k, planes - 1);
-      e[k] = in_range ? __ldcs(reinterpret_cast<const float4 *>(e_base + (size_t)p * Kp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      e[k] = __ldcs(reinterpret_cast<const float4 *>(e_base + (size_t)p * Kp));
     }
+    const float4 mean4 = s_nom4[p0 >> 2];  // warm start of the four planes (p0 is a multiple of 4): one LDS.128
+    const float means[4] = {mean4.x, mean4.y, mean4.z, mean4.w};
     float v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      // two controls: p0 is a multiple of 4, so the control index is k & 1 at compile time and the clamp bounds sit in
+      // registers (bounds01 = {lo0, hi0, lo1, hi1}); otherwise they come from the shared parameter block
       const int p = min(p0 + k, planes - 1);
-      const int u = p % U;
-      const float mean = s_nom[p], lo = sP.u_min[u], hi = sP.u_max[u];
+      const int u = U == 2 ? (k & 1) : p % U;
+      const float lo = U == 2 ? ((k & 1) ? bounds01.z : bounds01.x) : sP.u_min[u];
+      const float hi = U == 2 ? ((k & 1) ? bounds01.w : bounds01.y) : sP.u_max[u];
+      const float mean = means[k];  // planes past the end read the zero padding: their sums are never stored
       float a = wq.x * sample_control(e[k].x, sigma, mean, lo, hi);
       a = fmaf(wq.y, sample_control(e[k].y, sigma, mean, lo, hi), a);
       a = fmaf(wq.z, sample_control(e[k].z, sigma, mean, lo, hi), a);
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(128, MODEL == kFullBody ? MPPI_K2_MINBLOCKS_FB
   }
   const float m_cta = block_min_to_global(c, i < K, cmin + robot, s_red);
   if (cta_part == nullptr) return;  // kernel argument: uniform
-  cta_weighted_controls<MODEL>(sP, hdr->inv_lambda, c, i < K, m_cta, s_nom,
+  cta_weighted_controls<MODEL>(sP, make_float4(kb.lo[0], kb.hi[0], kb.lo[1], kb.hi[1]), hdr->inv_lambda, c, i < K, m_cta, s_nom,
                                eps + (size_t)par * buf_elems + (size_t)robot * planes * Kp, Kp, planes,
                                cta_part + ((size_t)robot * gridDim.x + blockIdx.x) * part_stride);
 }
