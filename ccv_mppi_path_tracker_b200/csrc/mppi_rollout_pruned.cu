@@ -32,6 +32,8 @@
 //                                    (+ the NVLink record exchange) in one launch
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "mppi_device.cuh"
 
 namespace mppi {
@@ -688,16 +690,23 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float4
   const float sigma = sP.sigma;
   const bool steer_off = MODEL == kFullBody && sP.steer_off;
   const float4 *s_nom4 = reinterpret_cast<const float4 *>(s_nom);  // 16-byte aligned, padded by 2 U >= 4 entries
+  const u64 sig2 = pack2(sigma, sigma), w01 = pack2(wq.x, wq.y), w23 = pack2(wq.z, wq.w);
   // a warp takes 4 consecutive planes at a time: 4 independent 16-byte loads per lane, then one transposing butterfly
   // reduces the 4 partial sums over the 32 lanes (lanes 0, 8, 16, 24 end up with one plane each); fixed order,
   // deterministic.  (Issuing the next four planes' loads ahead of the arithmetic, or 8 planes at a time, costs 12-18
   // registers -- one resident CTA per SM -- and gained nothing at K = 2^17 .. 2^20: measured, dropped.)
-  for (int p0 = wid * 4; p0 < planes; p0 += 16) {
+  // Full groups of four planes walk a running pointer (no per-load index arithmetic); the one ragged group at the end
+  // of the record (planes is not a multiple of 4 for every model / horizon) clamps its plane indices instead.
+  const size_t plane_stride = (size_t)Kp;
+  const bool up = lane & 16, up8 = lane & 8;
+  const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // value index held by this lane
+  auto group = [&](int p0, const float *ptr, auto full_tag) {
+    constexpr bool kFull = decltype(full_tag)::value;
     float4 e[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int p = min(p0 + k, planes - 1);
-      e[k] = __ldcs(reinterpret_cast<const float4 *>(e_base + (size_t)p * Kp));
+      const float *q = kFull ? ptr + k * plane_stride : e_base + (size_t)min(p0 + k, planes - 1) * plane_stride;
+      e[k] = __ldcs(reinterpret_cast<const float4 *>(q));
     }
     const float4 mean4 = s_nom4[p0 >> 2];  // warm start of the four planes (p0 is a multiple of 4): one LDS.128
     const float means[4] = {mean4.x, mean4.y, mean4.z, mean4.w};
@@ -706,19 +715,23 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float4
     for (int k = 0; k < 4; ++k) {
       // two controls: p0 is a multiple of 4, so the control index is k & 1 at compile time and the clamp bounds sit in
       // registers (bounds01 = {lo0, hi0, lo1, hi1}); otherwise they come from the shared parameter block
-      const int p = min(p0 + k, planes - 1);
-      const int u = U == 2 ? (k & 1) : p % U;
+      const int u = U == 2 ? (k & 1) : (p0 + k) % U;  // (a plane past the end is never stored)
       const float lo = U == 2 ? ((k & 1) ? bounds01.z : bounds01.x) : sP.u_min[u];
       const float hi = U == 2 ? ((k & 1) ? bounds01.w : bounds01.y) : sP.u_max[u];
-      const float mean = means[k];  // planes past the end read the zero padding: their sums are never stored
-      float a = wq.x * sample_control(e[k].x, sigma, mean, lo, hi);
-      a = fmaf(wq.y, sample_control(e[k].y, sigma, mean, lo, hi), a);
-      a = fmaf(wq.z, sample_control(e[k].z, sigma, mean, lo, hi), a);
-      a = fmaf(wq.w, sample_control(e[k].w, sigma, mean, lo, hi), a);
+      const float mean = means[k];  // planes past the end read the zero padding
+      // sample_control of the four samples, two at a time (FFMA2: the same fmaf per element, then the scalar clamp),
+      // and the weighted sum as two packed partial sums {w0 u0 + w2 u2, w1 u1 + w3 u3}
+      float r0, r1, r2, r3;
+      unpack2(fma2(pack2(e[k].x, e[k].y), sig2, pack2(mean, mean)), r0, r1);
+      unpack2(fma2(pack2(e[k].z, e[k].w), sig2, pack2(mean, mean)), r2, r3);
+      const u64 c01 = pack2(clamp_ref(r0, lo, hi), clamp_ref(r1, lo, hi));
+      const u64 c23 = pack2(clamp_ref(r2, lo, hi), clamp_ref(r3, lo, hi));
+      float a_lo, a_hi;
+      unpack2(fma2(c23, w23, mul2(c01, w01)), a_lo, a_hi);
+      const float a = a_lo + a_hi;
       v[k] = (steer_off && u == 2) ? 0.f : a;  // FB:517: every sample of that control is 0
     }
     // 4 values x 32 lanes -> lane l (l % 8 == 0) holds plane p0 + (l >> 3 with the two bits swapped: see idx)
-    const bool up = lane & 16;
     float r[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -726,14 +739,16 @@ __device__ __noinline__ void cta_weighted_controls(const SolveParams &sP, float4
       const float keep = up ? v[k + 2] : v[k];
       r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
-    const bool up8 = lane & 8;
     float r1 = (up8 ? r[1] : r[0]) + __shfl_xor_sync(0xffffffffu, up8 ? r[0] : r[1], 8);
     r1 += __shfl_xor_sync(0xffffffffu, r1, 4);
     r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
     r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-    const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // value index held by this lane
-    if ((lane & 7) == 0 && p0 + idx < planes) rec[4 + p0 + idx] = r1;
-  }
+    if ((lane & 7) == 0 && (kFull || p0 + idx < planes)) rec[4 + p0 + idx] = r1;
+  };
+  int p0 = wid * 4;
+  const float *ptr = e_base + (size_t)p0 * plane_stride;
+  for (; p0 + 4 <= planes; p0 += 16, ptr += 16 * plane_stride) group(p0, ptr, std::true_type{});
+  if (p0 < planes) group(p0, ptr, std::false_type{});  // warp-uniform: p0 depends on the warp index only
 }
 
 // K2 with the TMA ring.  Dynamic shared memory = ring [4 warps][kStages][rows][32] (1 KB aligned) | window pairs |
