@@ -265,14 +265,17 @@ bool fused_tail_for(mppi_handle h, const DeviceState &t) {
 //   plain stream launches (back-to-back throughput):
 //     main:  . . . . . . . . . . . . . . K2 -> (K3 -> K4 | -) -> tail (finalize / exchange / merge; counter++)
 //     side:  [K-1 window] -> K0 candidate grid -> K1 noise of the NEXT solve (prefetch)
-//     The side stream starts as soon as ITS inputs are there -- the staged pose / window of this solve and the end of
-//     the previous solve's last reader of window, grid and noise buffer -- so window builder, candidate grid and
-//     generator run under the previous solve's K4 / tail.  K2 waits for K0.
+//     The side stream starts as soon as ITS inputs are there -- the staged pose / window of this solve, the end of the
+//     last reader of this solve's window / grid slot (two solves ago: the slots alternate) and of the noise buffer --
+//     so window builder, candidate grid and generator run under the previous solve.  K2 waits for K0.
+//     K3, K4 and the tail are programmatic dependents of the kernel in front of them (the one-kernel tail only behind
+//     a single-wave K2), and K2 is a programmatic dependent of the PREVIOUS solve's tail: launch latency, header /
+//     window staging and barrier set-up overlap the predecessor (pdl_wait() in the kernels).
 //   inside a CUDA graph (the synchronous latency path; nothing of another solve to overlap with):
 //     main:  [K-1] -> K0 -> K2 -> (K3 -> K4 | -) -> tail          side:  K1 noise of the next solve
-//     K2, K3, K4 are programmatic dependents of the kernel in front of them: their launch latency and K2's input
-//     prologue overlap the predecessor (pdl_wait() in the kernels).
-// The tail waits for K1: the generator reads the solve counter that the tail advances.
+//     K2, K3, K4 and the tail are programmatic dependents of the kernel in front of them.
+// The generator keeps its own solve index on the device (counters[1]): nothing orders it against the tail, which
+// advances the solve counter; the NEXT solve's K2 waits for it (ev_join).
 #ifndef MPPI_K2_STREAM_PDL
 #define MPPI_K2_STREAM_PDL 1
 #endif

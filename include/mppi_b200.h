@@ -223,9 +223,9 @@ int mppi_last_launch_count(mppi_handle h);
 int mppi_comm_get_unique_id(void *id_out /* MPPI_COMM_ID_BYTES */);
 int mppi_comm_init(mppi_handle h, const void *id, int rank, int n_ranks);
 /* The same exchange without NCCL, over NVLink peer memory: every rank exports an exchange buffer (CUDA IPC handle,
- * MPPI_IPC_HANDLE_BYTES), the launcher all-gathers the handles, every rank connects.  Afterwards the finalize
- * kernel of a solve stores this rank's record straight into every peer's buffer and raises a flag there; the merge
- * kernel waits for the flags.  One process per GPU; every rank must call mppi_solve / mppi_enqueue the same number
+ * MPPI_IPC_HANDLE_BYTES), the launcher all-gathers the handles, every rank connects.  Afterwards the last kernel
+ * of a solve stores this rank's record straight into every peer's buffer -- 8-byte words {value, solve stamp}, so
+ * data and arrival travel in one store -- polls its own buffer for the peers' words and merges.  One process per GPU; every rank must call mppi_solve / mppi_enqueue the same number
  * of times, and the ranks should pass a barrier between mppi_comm_connect and their first solve.  A peer whose
  * record does not arrive within MPPI_OPT_EXCHANGE_TIMEOUT_MS (default 2 s, device-side) fails the solve: the warm
  * start keeps its previous value, and mppi_solve / mppi_download / mppi_synchronize return MPPI_ERR_NCCL. */
