@@ -60,6 +60,40 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(res["p2p_fused"], res["nccl_fused"])
     rng_ = np.array(case["sp"]["u_max"][:3]) - np.array(case["sp"]["u_min"][:3])
     assert (np.abs(res["p2p"] - res["p2p_fused"]) / rng_).max() < 5e-4  # per-CTA vs per-chunk summation order
+    # the general form of the exchange (several robots per handle; a record of more than 2 x 256 columns): every word
+    # polled in batches over the ranks, merge from the buffer -- against the NCCL all-gather + merge kernel, bit for bit
+    for model, Kg, Tg, Rg in (("steering", 2048, 40, 3), ("full_body", 1024, 120, 1)):
+        cg = make_case(model, Kg, Tg, seed=33)
+        states = np.tile(cg["state"], (Rg, 1))
+        states[:, 0] += 0.04 * np.arange(Rg)
+        got = {}
+        for mode in ("p2p", "nccl"):
+            ctl = CONTROLLERS[model](launch=True, n_robots=Rg, device=rank, horizon=Tg, num_samples=Kg // world,
+                                     **cg["overrides"])
+            for r in range(Rg):
+                ctl.set_path(cg["path"], robot=r)
+            ctl.set_seed(78, 0)
+            ctl.set_shard(rank * (Kg // world), Kg, 0)
+            if mode == "p2p":
+                t = torch.frombuffer(bytearray(ctl.comm_export(world)), dtype=torch.uint8).cuda()
+                allh = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allh, t)
+                ctl.comm_connect(b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh), rank, world)
+            else:
+                idt = torch.zeros(_capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(idt, 0)
+                ctl.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+            dist.barrier()
+            got[mode] = np.stack([np.array(ctl.solve(states, cg["dt"]), copy=True) for _ in range(3)])
+            dist.barrier()
+            ctl.close()
+        assert np.array_equal(got["p2p"], got["nccl"]), (model, Rg)
+        mine = torch.from_numpy(got["p2p"].copy()).cuda()
+        both = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert torch.equal(both[0], both[1]), (model, Rg)  # every rank holds the same controls
     # a peer that stops solving: the other rank's solve fails after MPPI_OPT_EXCHANGE_TIMEOUT_MS instead of merging
     # garbage, and its controls / warm start keep their previous values
     ctl = CONTROLLERS["steering"](launch=True, device=rank, horizon=T, num_samples=K // world)
