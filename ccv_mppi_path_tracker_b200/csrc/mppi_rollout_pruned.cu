@@ -140,10 +140,6 @@ __device__ __forceinline__ float scan_rest(float best, unsigned pairs_s, uint32_
   }
   return best;
 }
-__device__ __forceinline__ float scan_pairs(unsigned pairs_s, uint32_t e, float x, float y) {
-  const u64 xy = pack2(x, y);
-  return scan_rest(scan_first(pairs_s, e, xy), pairs_s, e, xy);
-}
 
 // The same scan, also returning the FIRST index that attains the minimum (-1 when no point is closer than the cap):
 // what the literal loop `if (d2 < best) { best = d2; arg = j; }` (DD:186-190) records.  Every point that can be
