@@ -238,3 +238,27 @@ def test_circle_path_generator():
     assert np.allclose(p[:, 0], 1.0 + 2.0 * np.cos(s), atol=1e-9) and np.allclose(p[:, 1], -0.5 + 2.0 * np.sin(s) + 2.0, atol=1e-9)
     assert np.allclose(np.hypot(p[:, 0] - 1.0, p[:, 1] - 1.5), 2.0)
     assert np.array_equal(p[0], [3.0, 1.5])
+
+
+def test_shipped_library_contains_the_blackwell_instructions():
+    """The built libmppi_b200.so (sm_100a SASS, read with cuobjdump here on the CPU) really contains what DESIGN.md
+    claims for the production rollout kernel: TMA tensor loads + mbarrier waits, packed FP32, three-input min,
+    programmatic-dependent-launch instructions -- and no sm_90-only or library kernels."""
+    import shutil
+    import subprocess
+    from ccv_mppi_path_tracker_b200 import _capi
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper() or "sm_100" in sass
+    # split per function, pick the production K2 instantiation (diff drive, no tap)
+    parts = sass.split("Function : ")
+    k2 = [p for p in parts if p.startswith("_ZN4mppi23rollout_cost_tma_kernelILi0ELb0E")]
+    assert len(k2) == 1
+    body = k2[0]
+    for mnemonic in ("UTMALDG", "SYNCS", "ELECT", "FFMA2", "FMUL2", "FADD2", "FMNMX3", "VIMNMX", "ACQBULK", "PREEXIT"):
+        assert mnemonic in body, mnemonic
+    assert "WGMMA" not in sass and "HGMMA" not in sass  # nothing sm_90-only, no tensor-core library code
+    names = [p.split("\n", 1)[0] for p in parts[1:]]
+    assert all(n.startswith("_ZN4mppi") for n in names), [n for n in names if not n.startswith("_ZN4mppi")]
